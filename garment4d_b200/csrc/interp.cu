@@ -1,0 +1,121 @@
+// three_nn / three_interpolate (feature propagation) for sm_100a.
+//
+// Replaces (reference, modules/pointnet2/pointnet2/src/interpolate_gpu.cu):
+//   three_nn_kernel_fast               :9-52    (thread per unknown point, known cloud re-read from L1)
+//   three_interpolate_kernel_fast      :77-97   (thread per (c, n): idx/weight re-read once per channel)
+//   three_interpolate_grad_kernel_fast :120-142
+// Here the known cloud is staged in shared memory tiles, and interpolation loads idx/weight once per
+// point and loops over a channel slab.  Arithmetic order matches the reference build bit for bit:
+// d = fma(dz,dz,fma(dx,dx,dy*dy)) with dx = u - k, strict '<' insertion (lowest index wins ties),
+// out = fma(w2,p2, fma(w0,p0, w1*p1)).
+#include "common.cuh"
+
+namespace g4d {
+
+constexpr int NN_TILE = 1024;
+
+__global__ void __launch_bounds__(256)
+three_nn_kernel(int n, int m, const float* __restrict__ unknown_all, const float* __restrict__ known_all,
+                float* __restrict__ dist2_all, int* __restrict__ idx_all) {
+    __shared__ float tile[NN_TILE * 3];
+    const size_t bi = blockIdx.y;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = pt < n;
+    const float* u = unknown_all + (bi * n + (live ? pt : 0)) * 3;
+    const float* known = known_all + bi * (size_t)m * 3;
+    const float ux = __ldg(u), uy = __ldg(u + 1), uz = __ldg(u + 2);
+    // the reference keeps running bests in double initialised to 1e40; a float distance compares
+    // against them exactly like against +inf, and (float)1e40 == +inf is what it stores when m < 3.
+    float best1 = INFINITY, best2 = INFINITY, best3 = INFINITY;
+    int besti1 = 0, besti2 = 0, besti3 = 0;
+    for (int base = 0; base < m; base += NN_TILE) {
+        const int tn = min(NN_TILE, m - base);
+        __syncthreads();
+        for (int e = threadIdx.x; e < tn * 3; e += blockDim.x) tile[e] = __ldg(known + (size_t)base * 3 + e);
+        __syncthreads();
+        for (int k = 0; k < tn; ++k) {
+            const float d = sqdist_ref(ux - tile[3 * k], uy - tile[3 * k + 1], uz - tile[3 * k + 2]);   // broadcast reads
+            if (d < best1) {
+                best3 = best2; besti3 = besti2;
+                best2 = best1; besti2 = besti1;
+                best1 = d; besti1 = base + k;
+            } else if (d < best2) {
+                best3 = best2; besti3 = besti2;
+                best2 = d; besti2 = base + k;
+            } else if (d < best3) {
+                best3 = d; besti3 = base + k;
+            }
+        }
+    }
+    if (live) {
+        float* od = dist2_all + (bi * n + pt) * 3;
+        int* oi = idx_all + (bi * n + pt) * 3;
+        od[0] = best1; od[1] = best2; od[2] = best3;
+        oi[0] = besti1; oi[1] = besti2; oi[2] = besti3;
+    }
+}
+
+__global__ void three_interpolate_kernel(int c, int m, int n, const float* __restrict__ points, const int* __restrict__ idx,
+                                         const float* __restrict__ weight, float* __restrict__ out) {
+    const size_t bi = blockIdx.z;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= n) return;
+    const int* id = idx + (bi * n + pt) * 3;
+    const float* w = weight + (bi * n + pt) * 3;
+    const int i0 = __ldg(id), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+    const float w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    for (int ci = blockIdx.y; ci < c; ci += gridDim.y) {
+        const float* p = points + (bi * c + ci) * (size_t)m;
+        out[(bi * c + ci) * (size_t)n + pt] = __fmaf_rn(w2, __ldg(p + i2), __fmaf_rn(w0, __ldg(p + i0), __fmul_rn(w1, __ldg(p + i1))));
+    }
+}
+
+__global__ void three_interpolate_grad_kernel(int c, int n, int m, const float* __restrict__ grad_out, const int* __restrict__ idx,
+                                              const float* __restrict__ weight, float* __restrict__ grad_points) {
+    const size_t bi = blockIdx.z;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= n) return;
+    const int* id = idx + (bi * n + pt) * 3;
+    const float* w = weight + (bi * n + pt) * 3;
+    const int i0 = __ldg(id), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+    const float w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    for (int ci = blockIdx.y; ci < c; ci += gridDim.y) {
+        const float g = __ldg(grad_out + (bi * c + ci) * (size_t)n + pt);
+        float* gp = grad_points + (bi * c + ci) * (size_t)m;
+        atomicAdd(gp + i0, g * w0);
+        atomicAdd(gp + i1, g * w1);
+        atomicAdd(gp + i2, g * w2);
+    }
+}
+
+}  // namespace g4d
+
+using namespace g4d;
+
+// three_nn_kernel_launcher_fast (interpolate_gpu.h:16-17).  Writes SQUARED distances, like the reference kernel.
+G4D_API int g4d_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx, void* stream) {
+    if (b < 0 || n < 0 || m < 0) return bad_arg("three_nn: negative size");
+    if (b == 0 || n == 0) return 0;
+    if (!unknown || !dist2 || !idx || (m > 0 && !known)) return bad_arg("three_nn: null pointer");
+    dim3 grid((n + 255) / 256, b);
+    three_nn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+    return finish_launch("g4d three_nn");
+}
+
+// three_interpolate_kernel_launcher_fast (interpolate_gpu.h:21-22)
+G4D_API int g4d_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx, const float* weight, float* out, void* stream) {
+    if (b < 0 || c < 0 || n < 0) return bad_arg("three_interpolate: negative size");
+    if (b == 0 || c == 0 || n == 0) return 0;
+    dim3 grid((n + 255) / 256, c < 16 ? c : 16, b);
+    three_interpolate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, m, n, points, idx, weight, out);
+    return finish_launch("g4d three_interpolate");
+}
+
+// three_interpolate_grad_kernel_launcher_fast (interpolate_gpu.h:27-28); grad_points pre-zeroed by the caller.
+G4D_API int g4d_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out, const int* idx, const float* weight, float* grad_points, void* stream) {
+    if (b < 0 || c < 0 || n < 0) return bad_arg("three_interpolate_grad: negative size");
+    if (b == 0 || c == 0 || n == 0) return 0;
+    dim3 grid((n + 255) / 256, c < 16 ? c : 16, b);
+    three_interpolate_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, m, grad_out, idx, weight, grad_points);
+    return finish_launch("g4d three_interpolate_grad");
+}

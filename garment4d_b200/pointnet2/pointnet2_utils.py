@@ -1,0 +1,284 @@
+"""The reference's point-cloud operators (modules/pointnet2/pointnet2/pointnet2_utils.py) on the B200 kernels.
+
+Same public names, argument order, shapes, dtypes and autograd contract as the reference:
+
+    furthest_point_sample(xyz, npoint) -> idx (B,npoint) int32            non-differentiable
+    gather_operation(features (B,C,N), idx (B,m)) -> (B,C,m)              grad w.r.t. features
+    three_nn(unknown (B,n,3), known (B,m,3)) -> (dist (B,n,3), idx)       non-differentiable
+    three_interpolate(features (B,C,m), idx, weight) -> (B,C,n)           grad w.r.t. features
+    grouping_operation(features (B,C,N), idx (B,P,S)) -> (B,C,P,S)        grad w.r.t. features
+    ball_query(radius, nsample, xyz, new_xyz) -> idx (B,P,nsample) int32  non-differentiable
+    QueryAndGroup(radius, nsample, use_xyz)(xyz, new_xyz, features)       -> (B, 3+C, P, nsample)
+    GroupAll(use_xyz)(xyz, new_xyz, features)                             -> (B, 3+C, 1, N)
+
+The nine low-level calls go through ``garment4d_b200.pointnet2_cuda`` (the mirror of the reference's compiled
+module).  Two fused entry points are added behind the same operators:
+``furthest_point_sample_and_gather`` (FPS + centroid gather, one launch) and the single-kernel
+``QueryAndGroup.forward``.
+"""
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from .. import _lib
+from .. import pointnet2_cuda as pointnet2
+
+
+def _i32(*shape, device):
+    return torch.empty(*shape, dtype=torch.int32, device=device)
+
+
+def _f32(*shape, device):
+    return torch.empty(*shape, dtype=torch.float32, device=device)
+
+
+class FurthestPointSampling(Function):
+    @staticmethod
+    def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+        """xyz (B,N,3) -> (B,npoint) int32 indices; idx[:,0] == 0 (pointnet2_utils.py:10-29)."""
+        assert xyz.is_contiguous()
+        B, N, _ = xyz.size()
+        output = _i32(B, npoint, device=xyz.device)
+        temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
+        pointnet2.furthest_point_sampling_wrapper(B, N, npoint, xyz, temp, output)
+        ctx.mark_non_differentiable(output)
+        return output
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None
+
+
+furthest_point_sample = FurthestPointSampling.apply
+
+
+def furthest_point_sample_and_gather(xyz: torch.Tensor, npoint: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused FPS + gather: (idx (B,npoint) int32, new_xyz (B,npoint,3)).  Same indices as furthest_point_sample;
+    new_xyz == gather_operation(xyz^T, idx)^T bit for bit (a copy).  No gradient flows to xyz (as in the reference,
+    where new_xyz comes out of gather_operation applied to a non-differentiable index)."""
+    assert xyz.is_contiguous() and xyz.dtype == torch.float32 and xyz.is_cuda
+    B, N, _ = xyz.size()
+    idx = _i32(B, npoint, device=xyz.device)
+    new_xyz = _f32(B, npoint, 3, device=xyz.device)
+    scratch = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device) if N > 16384 else None
+    rc = _lib.lib().g4d_fps_gather(B, N, npoint, _lib.ptr(xyz), _lib.ptr(idx), _lib.ptr(new_xyz), _lib.ptr(scratch),
+                                   _lib.stream_ptr())
+    _lib.check(rc, "g4d_fps_gather")
+    return idx, new_xyz
+
+
+class GatherOperation(Function):
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        """(B,C,N), (B,npoint) -> (B,C,npoint)  (pointnet2_utils.py:42-60)"""
+        assert features.is_contiguous()
+        assert idx.is_contiguous()
+        B, npoint = idx.size()
+        _, C, N = features.size()
+        output = _f32(B, C, npoint, device=features.device)
+        pointnet2.gather_points_wrapper(B, C, N, npoint, features, idx, output)
+        ctx.for_backwards = (idx, C, N)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, C, N = ctx.for_backwards
+        B, npoint = idx.size()
+        grad_features = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+        pointnet2.gather_points_grad_wrapper(B, C, N, npoint, grad_out.contiguous(), idx, grad_features)
+        return grad_features, None
+
+
+gather_operation = GatherOperation.apply
+
+
+class ThreeNN(Function):
+    @staticmethod
+    def forward(ctx, unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (dist (B,n,3) = sqrt of squared distances, idx (B,n,3) int32)  (pointnet2_utils.py:78-98)"""
+        assert unknown.is_contiguous()
+        assert known.is_contiguous()
+        B, N, _ = unknown.size()
+        m = known.size(1)
+        dist2 = _f32(B, N, 3, device=unknown.device)
+        idx = _i32(B, N, 3, device=unknown.device)
+        pointnet2.three_nn_wrapper(B, N, m, unknown, known, dist2, idx)
+        ctx.mark_non_differentiable(idx)
+        return torch.sqrt(dist2), idx
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None
+
+
+three_nn = ThreeNN.apply
+
+
+class ThreeInterpolate(Function):
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        """features (B,C,m), idx/weight (B,n,3) -> (B,C,n)  (pointnet2_utils.py:110-131)"""
+        assert features.is_contiguous()
+        assert idx.is_contiguous()
+        assert weight.is_contiguous()
+        B, c, m = features.size()
+        n = idx.size(1)
+        ctx.three_interpolate_for_backward = (idx, weight, m)
+        output = _f32(B, c, n, device=features.device)
+        pointnet2.three_interpolate_wrapper(B, c, m, n, features, idx, weight, output)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        idx, weight, m = ctx.three_interpolate_for_backward
+        B, c, n = grad_out.size()
+        grad_features = torch.zeros(B, c, m, dtype=torch.float32, device=grad_out.device)
+        pointnet2.three_interpolate_grad_wrapper(B, c, n, m, grad_out.contiguous(), idx, weight, grad_features)
+        return grad_features, None, None
+
+
+three_interpolate = ThreeInterpolate.apply
+
+
+class GroupingOperation(Function):
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        """features (B,C,N), idx (B,npoint,nsample) -> (B,C,npoint,nsample)  (pointnet2_utils.py:158-176)"""
+        assert features.is_contiguous()
+        assert idx.is_contiguous()
+        B, nfeatures, nsample = idx.size()
+        _, C, N = features.size()
+        output = _f32(B, C, nfeatures, nsample, device=features.device)
+        pointnet2.group_points_wrapper(B, C, N, nfeatures, nsample, features, idx, output)
+        ctx.for_backwards = (idx, N)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        idx, N = ctx.for_backwards
+        B, C, npoint, nsample = grad_out.size()
+        grad_features = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+        pointnet2.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.contiguous(), idx, grad_features)
+        return grad_features, None
+
+
+grouping_operation = GroupingOperation.apply
+
+
+class BallQuery(Function):
+    @staticmethod
+    def forward(ctx, radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+        """-> idx (B,npoint,nsample) int32; all-zero row when no point is in range  (pointnet2_utils.py:202-222)"""
+        assert new_xyz.is_contiguous()
+        assert xyz.is_contiguous()
+        B, N, _ = xyz.size()
+        npoint = new_xyz.size(1)
+        idx = torch.zeros(B, npoint, nsample, dtype=torch.int32, device=xyz.device)
+        pointnet2.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None
+
+
+ball_query = BallQuery.apply
+
+
+def ball_query_pair(radius0, nsample0, radius1, nsample1, xyz, new_xyz):
+    """Both scales of an MSG module from one scan of the cloud (g4d_ball_query2); each result equals ball_query's."""
+    assert xyz.is_contiguous() and new_xyz.is_contiguous()
+    B, N, _ = xyz.size()
+    P = new_xyz.size(1)
+    idx0 = torch.zeros(B, P, nsample0, dtype=torch.int32, device=xyz.device)
+    idx1 = torch.zeros(B, P, nsample1, dtype=torch.int32, device=xyz.device)
+    rc = _lib.lib().g4d_ball_query2(B, N, P, float(radius0), nsample0, _lib.ptr(idx0), float(radius1), nsample1,
+                                    _lib.ptr(idx1), _lib.ptr(new_xyz), _lib.ptr(xyz), _lib.stream_ptr())
+    _lib.check(rc, "g4d_ball_query2")
+    return idx0, idx1
+
+
+_FUSED_NSAMPLE = (4, 8, 16, 32, 64, 128)
+
+
+class _QueryAndGroupFused(Function):
+    """QueryAndGroup.forward as ONE kernel.  Backward reproduces the reference graph: features and xyz receive the
+    scatter-add of the grouped gradient (GroupingOperation.backward), new_xyz receives minus the sum over samples
+    (the in-place ``grouped_xyz -= new_xyz`` of pointnet2_utils.py:253)."""
+
+    @staticmethod
+    def forward(ctx, radius, nsample, use_xyz, xyz, new_xyz, features):
+        B, N, _ = xyz.size()
+        P = new_xyz.size(1)
+        C = 0 if features is None else features.size(1)
+        cout = (3 if use_xyz else 0) + C
+        idx = _i32(B, P, nsample, device=xyz.device)
+        out = _f32(B, cout, P, nsample, device=xyz.device)
+        rc = _lib.lib().g4d_query_and_group(B, N, P, C, float(radius), nsample, int(use_xyz), _lib.ptr(xyz), _lib.ptr(new_xyz),
+                                            _lib.ptr(features), _lib.ptr(idx), _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(rc, "g4d_query_and_group")
+        ctx.meta = (idx, N, C, use_xyz)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, N, C, use_xyz = ctx.meta
+        B, _, P, S = grad_out.size()
+        grad_out = grad_out.contiguous()
+        g_xyz = g_new = g_feat = None
+        off = 0
+        if use_xyz:
+            gx = grad_out[:, :3].contiguous()
+            if ctx.needs_input_grad[3]:
+                g = torch.zeros(B, 3, N, dtype=torch.float32, device=grad_out.device)
+                pointnet2.group_points_grad_wrapper(B, 3, N, P, S, gx, idx, g)
+                g_xyz = g.transpose(1, 2).contiguous()
+            if ctx.needs_input_grad[4]:
+                g_new = -gx.sum(dim=3).transpose(1, 2).contiguous()
+            off = 3
+        if C > 0 and ctx.needs_input_grad[5]:
+            gf = grad_out[:, off:].contiguous()
+            g_feat = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+            pointnet2.group_points_grad_wrapper(B, C, N, P, S, gf, idx, g_feat)
+        return None, None, None, g_xyz, g_new, g_feat
+
+
+class QueryAndGroup(nn.Module):
+    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+        """radius of the ball, maximum number of neighbours, whether to prepend the relative xyz (pointnet2_utils.py:233-240)"""
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None) -> torch.Tensor:
+        """xyz (B,N,3), new_xyz (B,npoint,3), features (B,C,N) or None -> (B, 3+C, npoint, nsample)"""
+        if features is None:
+            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+        if self.nsample in _FUSED_NSAMPLE and xyz.is_contiguous() and new_xyz.is_contiguous() and (
+                features is None or features.is_contiguous()):
+            return _QueryAndGroupFused.apply(self.radius, self.nsample, self.use_xyz, xyz, new_xyz, features)
+        # generic composition, operator by operator (pointnet2_utils.py:250-265)
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        xyz_trans = xyz.transpose(1, 2).contiguous()
+        grouped_xyz = grouping_operation(xyz_trans, idx)
+        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+        if features is not None:
+            grouped_features = grouping_operation(features.contiguous(), idx)
+            return torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        return grouped_xyz
+
+
+class GroupAll(nn.Module):
+    def __init__(self, use_xyz: bool = True):
+        super().__init__()
+        self.use_xyz = use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        """xyz (B,N,3), features (B,C,N) -> (B, C+3, 1, N); new_xyz ignored (pointnet2_utils.py:273-291)"""
+        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
+        if features is not None:
+            grouped_features = features.unsqueeze(2)
+            return torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        return grouped_xyz

@@ -1,0 +1,144 @@
+/*
+ * garment4d_b200 -- C ABI of the B200 (sm_100a) implementation of Garment4D's data-parallel hot path.
+ *
+ * This header is the drop-in boundary.  Every entry point takes plain device pointers, sizes and a
+ * CUDA stream (passed as void*, i.e. a cudaStream_t; NULL = default stream), launches asynchronously
+ * on that stream, allocates nothing, keeps no state, and returns a cudaError_t as int (0 = success);
+ * g4d_last_error() gives the text.  All floats are IEEE fp32, all indices int32, all tensors
+ * contiguous, in the reference's layouts: coordinates (B,N,3), features channel-major (B,C,N),
+ * neighbourhood indices (B,P,K).  The current CUDA device must be the one that owns the pointers
+ * (as in the reference, which takes at::cuda::getCurrentCUDAStream() without a device guard).
+ *
+ * Section 1 mirrors, one to one, the kernel launchers that the reference's Python extension
+ * `pointnet2_cuda` binds (modules/pointnet2/pointnet2/src/pointnet2_api.cpp:10-23); the caller-side
+ * pre-conditions are the reference's: FPS `temp` pre-filled with 1e10 (pointnet2_utils.py:26),
+ * ball-query `idx` zero-filled (:218), *_grad outputs zero-filled (:67,146,190).
+ * Section 2 holds the fused forms that sit behind the same Python operators/modules.
+ * Section 3 is SMPL linear-blend skinning (smplx/smplx/lbs.py).
+ *
+ * Unlike the reference, a failed launch never calls exit(-1) (e.g. sampling_gpu.cu:39-43): it
+ * returns the error and the Python layer raises.
+ */
+#ifndef GARMENT4D_B200_H
+#define GARMENT4D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- 0. plumbing ------------------------------------------------------------------------------- */
+const char* g4d_last_error(void);       /* text of the calling thread's last failure */
+int g4d_abi_version(void);
+int g4d_sm_count(void);
+
+/* ---- 1. one-to-one replacements of the reference launchers ------------------------------------- */
+
+/* furthest_point_sampling_kernel_launcher  (sampling_gpu.h:26-27, sampling_gpu.cu:211-253; bound at
+ * sampling.cpp:36-46).  xyz (b,n,3) -> idx (b,m); temp (b,n) in/out scratch.  Bit-exact indices,
+ * including the reference's tie-break order (bit-reversed thread slot of its shared-memory tree). */
+int g4d_furthest_point_sampling(int b, int n, int m, const float* xyz, float* temp, int* idx, void* stream);
+
+/* gather_points_kernel_launcher_fast  (sampling_gpu.h:14-15, sampling_gpu.cu:26-43; sampling.cpp:11-21).
+ * out[b,c,j] = points[b,c,idx[b,j]] */
+int g4d_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx, float* out, void* stream);
+
+/* gather_points_grad_kernel_launcher_fast  (sampling_gpu.h:20-21, sampling_gpu.cu:65-83; sampling.cpp:24-34) */
+int g4d_gather_points_grad(int b, int c, int n, int npoints, const float* grad_out, const int* idx, float* grad_points, void* stream);
+
+/* ball_query_kernel_launcher_fast  (ball_query_gpu.h:12-13, ball_query_gpu.cu:48-67; ball_query.cpp:14-25).
+ * NOTE argument order: new_xyz (b,m,3) BEFORE xyz (b,n,3), as at the reference call site.
+ * idx (b,m,nsample): first nsample points with d^2 < radius^2 in ascending index order, padded with the
+ * first hit; rows without any hit are not written.  Bit-exact. */
+int g4d_ball_query(int b, int n, int m, float radius, int nsample, const float* new_xyz, const float* xyz, int* idx, void* stream);
+
+/* group_points_kernel_launcher_fast  (group_points_gpu.h:13-14, group_points_gpu.cu:69-86; group_points.cpp:25-36).
+ * out[b,c,p,s] = points[b,c,idx[b,p,s]] */
+int g4d_group_points(int b, int c, int n, int npoints, int nsample, const float* points, const int* idx, float* out, void* stream);
+
+/* group_points_grad_kernel_launcher_fast  (group_points_gpu.h:19-20, group_points_gpu.cu:28-44; group_points.cpp:11-22) */
+int g4d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float* grad_out, const int* idx, float* grad_points, void* stream);
+
+/* three_nn_kernel_launcher_fast  (interpolate_gpu.h:16-17, interpolate_gpu.cu:55-74; interpolate.cpp:14-23).
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) SQUARED distances, idx (b,n,3).  Bit-exact. */
+int g4d_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx, void* stream);
+
+/* three_interpolate_kernel_launcher_fast  (interpolate_gpu.h:21-22, interpolate_gpu.cu:99-117; interpolate.cpp:26-39).
+ * points (b,c,m), idx/weight (b,n,3) -> out (b,c,n).  Bit-exact (same FMUL/FFMA order). */
+int g4d_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx, const float* weight, float* out, void* stream);
+
+/* three_interpolate_grad_kernel_launcher_fast  (interpolate_gpu.h:27-28, interpolate_gpu.cu:144-161; interpolate.cpp:42-54) */
+int g4d_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out, const int* idx, const float* weight, float* grad_points, void* stream);
+
+/* ---- 2. fused forms (behind the same Python operators / nn.Modules) ----------------------------- */
+
+/* FPS + centroid gather in one launch: idx (b,m) and new_xyz (b,m,3).  Replaces
+ * furthest_point_sample -> gather_operation -> two transpose().contiguous() copies
+ * (pointnet2_modules.py:30-35).  scratch (b,n) floats pre-filled with 1e10 is needed only for n > 16384. */
+int g4d_fps_gather(int b, int n, int m, const float* xyz, int* idx, float* new_xyz, float* scratch, void* stream);
+
+/* Two ball queries (the two scales of a PointnetSAModuleMSG, pointnet2_modules.py:37-38) from ONE scan. */
+int g4d_ball_query2(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
+                    const float* new_xyz, const float* xyz, void* stream);
+
+/* QueryAndGroup.forward (pointnet2_utils.py:243-265) as one kernel: ball query + group(xyz) - centroid +
+ * group(features) + cat.  features (b,c,n) may be NULL with c = 0.  out: (b, 3+c, m, nsample) when use_xyz,
+ * else (b, c, m, nsample).  idx (b,m,nsample) optional output (no-hit rows written as zeros).
+ * nsample in {4,8,16,32,64,128}. */
+int g4d_query_and_group(int b, int n, int m, int c, float radius, int nsample, int use_xyz, const float* xyz,
+                        const float* new_xyz, const float* features, int* idx, float* out, void* stream);
+
+/* Grouped shared-MLP + max-pool on the tcgen05 tensor cores: for every centroid p, gathers its nsample
+ * neighbours' [xyz - centroid, features] rows, runs the 3-layer 1x1-conv MLP (eval-mode BatchNorm folded
+ * into weight/bias, ReLU) and max-pools over the neighbourhood -- SharedMLP + F.max_pool2d of
+ * _PointnetSAModuleBase.forward (pointnet2_modules.py:37-51; pytorch_utils.py:5-32) without ever
+ * materialising the (b, C, m, nsample) grouped tensor.  See g4d_sa_mlp_* below. */
+typedef struct g4d_sa_mlp_desc {
+    int c_in;          /* feature channels of the source points (0 = xyz only)                      */
+    int c1, c2, c3;    /* MLP widths; c1,c2 multiples of 16 and <= 256; c3 <= 256                   */
+    int nsample;       /* neighbourhood size: 16, 32, 64 or 128                                     */
+    int k0;            /* padded input width of layer 1 in fp16 elements (from g4d_sa_mlp_k0)       */
+} g4d_sa_mlp_desc;
+
+/* Padded layer-1 K for a given c_in (9 split-precision xyz slots + c_in, rounded up to 16). */
+int g4d_sa_mlp_k0(int c_in);
+/* Bytes of the packed parameter blob (fp16 UMMA-canonical weights + fp32 biases) for a descriptor. */
+size_t g4d_sa_mlp_param_bytes(const g4d_sa_mlp_desc* d);
+/* Packs host fp32 folded weights w1 (c1, 3+c_in), w2 (c2,c1), w3 (c3,c2) and biases into `blob` (host memory). */
+int g4d_sa_mlp_pack_params(const g4d_sa_mlp_desc* d, const float* w1, const float* b1, const float* w2, const float* b2,
+                           const float* w3, const float* b3, void* blob);
+/* xyz (b,n,3), new_xyz (b,m,3), idx (b,m,nsample), feat_pm: point-major fp16 features (b,n,c_in) or NULL.
+ * out_cm: fp32 channel-major (b, out_c_total, m) written at channel offset out_c_off (fuses the torch.cat of
+ * the MSG branches, pointnet2_modules.py:55); out_pm: optional fp16 point-major (b, m, out_c_total) copy for
+ * the next level's gather (may be NULL). */
+int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int b, int n, int m, const float* xyz,
+                   const float* new_xyz, const int* idx, const void* feat_pm, float* out_cm, void* out_pm,
+                   int out_c_total, int out_c_off, void* stream);
+
+/* ---- 3. SMPL linear-blend skinning (smplx/smplx/lbs.py) ----------------------------------------- */
+
+/* batch_rodrigues (lbs.py:312-346): rot_vecs (n,3) -> rot_mats (n,3,3) */
+int g4d_batch_rodrigues(int n, const float* rot_vecs, float* rot_mats, void* stream);
+/* vertices2joints / vertices2jointsB (lbs.py:251-286): J_regressor (J,V) or, per_frame_regressor=1, (F,J,V) */
+int g4d_vertices2joints(int F, int V, int J, int per_frame_regressor, const float* J_regressor, const float* vertices,
+                        float* joints, void* stream);
+/* batch_rigid_transform (lbs.py:362-419): rot_mats (F,J,3,3), joints (F,J,3), parents int32 (J) ->
+ * posed_joints (F,J,3), rel_transforms (F,J,4,4) */
+int g4d_batch_rigid_transform(int F, int J, const float* rot_mats, const float* joints, const int* parents,
+                              float* posed_joints, float* rel_transforms, void* stream);
+/* skinning tail (lbs.py:233-246): verts = (W.A)[v_posed;1]; W (V,J) or, per_frame_weights=1, (F,V,J) */
+int g4d_lbs_skin(int F, int V, int J, int per_frame_weights, const float* v_posed, const float* A, const float* W,
+                 float* verts, void* stream);
+/* full lbs() (lbs.py:152-248); ws = device scratch of g4d_lbs_workspace_bytes(F,V,J) */
+size_t g4d_lbs_workspace_bytes(int F, int V, int J);
+int g4d_lbs(int F, int V, int J, int NB, int betas_rows, int pose2rot, const float* betas, const float* pose,
+            const float* v_template, const float* shapedirs, const float* posedirs, const float* J_regressor,
+            const int* parents, const float* lbs_weights, float* verts, float* joints, void* ws, size_t ws_bytes,
+            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GARMENT4D_B200_H */

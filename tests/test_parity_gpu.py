@@ -1,0 +1,184 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI / the pointnet2_cuda mirror) against
+  (1) the CPU oracle (oracle/pointnet2_oracle.c), bit-exact for indices, and
+  (2) the reference's own kernels compiled unmodified (oracle/_ref), when that library travelled with the repo.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pointnet2 as orc
+from oracle import refgpu
+from tests.util import clouds
+
+pytestmark = pytest.mark.gpu
+
+from garment4d_b200.pointnet2 import pointnet2_utils as pu   # noqa: E402
+
+CASES = [  # (seed, B, N, m, radius, K)
+    (1, 2, 1024, 256, 0.2, 32),      # BASELINE config 1
+    (2, 3, 1000, 200, 0.15, 16),     # bs = 512 < N
+    (3, 2, 37, 9, 0.5, 8),           # tiny
+    (4, 1, 300, 300, 0.3, 64),       # m == N
+    (5, 2, 2048, 512, 0.1, 16),
+    (6, 2, 4096, 256, 0.07, 32),
+    (7, 2, 8192, 1024, 0.1, 32),     # SA1b
+    (8, 1, 6890, 1024, 0.05, 16),    # the reference's real N
+    (9, 1, 16384, 1024, 0.05, 16),   # config 5 cloud size
+    (10, 1, 20000, 128, 0.05, 16),   # generic path (N > 16384)
+]
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.parametrize("kind", ["cube", "body"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"N{c[2]}m{c[3]}")
+def test_fps_ball_group_vs_oracle(cuda, case, kind):
+    seed, B, N, m, radius, K = case
+    xyz = clouds(seed, B, N, kind)
+    x = _t(xyz, cuda)
+    # FPS: drop-in op, fused op, oracle, reference kernels
+    idx = pu.furthest_point_sample(x, m)
+    idx_f, new_xyz_f = pu.furthest_point_sample_and_gather(x, m)
+    want = orc.furthest_point_sample(xyz, m)
+    assert np.array_equal(idx.cpu().numpy(), want), "FPS indices differ from the oracle"
+    assert torch.equal(idx, idx_f)
+    new_xyz = pu.gather_operation(x.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+    assert torch.equal(new_xyz, new_xyz_f)
+    assert np.array_equal(new_xyz.cpu().numpy(), orc.gather_operation(xyz.transpose(0, 2, 1), want).transpose(0, 2, 1))
+    if refgpu.available():
+        assert torch.equal(idx, refgpu.furthest_point_sample(x, m)), "FPS differs from the reference kernel"
+    # ball query (+ the two-scale scan)
+    bq = pu.ball_query(radius, K, x, new_xyz)
+    want_bq = orc.ball_query(radius, K, xyz, new_xyz.cpu().numpy())
+    assert np.array_equal(bq.cpu().numpy(), want_bq), "ball_query differs from the oracle"
+    bq0, bq1 = pu.ball_query_pair(radius, K, radius * 0.5, max(K // 2, 1), x, new_xyz)
+    assert torch.equal(bq0, bq)
+    assert np.array_equal(bq1.cpu().numpy(), orc.ball_query(radius * 0.5, max(K // 2, 1), xyz, new_xyz.cpu().numpy()))
+    if refgpu.available():
+        assert torch.equal(bq, refgpu.ball_query(radius, K, x, new_xyz)), "ball_query differs from the reference kernel"
+    # group + fused QueryAndGroup
+    C = 5
+    feats = np.random.RandomState(seed + 100).randn(B, C, N).astype(np.float32)
+    f = _t(feats, cuda)
+    g = pu.grouping_operation(f, bq)
+    assert np.array_equal(g.cpu().numpy(), orc.grouping_operation(feats, want_bq))
+    if K in (4, 8, 16, 32, 64, 128):
+        qg = pu.QueryAndGroup(radius, K)(x, new_xyz, f)
+        want_qg = orc.query_and_group(radius, K, xyz, new_xyz.cpu().numpy(), feats)
+        assert np.array_equal(qg.cpu().numpy(), want_qg), "fused QueryAndGroup differs from the oracle"
+        qg0 = pu.QueryAndGroup(radius, K)(x, new_xyz, None)
+        assert np.array_equal(qg0.cpu().numpy(), want_qg[:, :3])
+
+
+def test_ball_query_no_hit_rows_stay_zero(cuda):
+    xyz = clouds(11, 2, 512, "cube")
+    q = xyz[:, :16].copy() + np.float32(10.0)          # far away: no hits
+    idx = pu.ball_query(0.05, 8, _t(xyz, cuda), _t(q, cuda))
+    assert int(idx.abs().sum()) == 0
+    assert np.array_equal(idx.cpu().numpy(), orc.ball_query(0.05, 8, xyz, q))
+
+
+@pytest.mark.parametrize("case", [(21, 2, 1024, 256), (22, 2, 8192, 1024), (23, 1, 300, 2), (24, 2, 256, 64), (25, 1, 1000, 1500)],
+                         ids=lambda c: f"n{c[2]}m{c[3]}")
+def test_three_nn_interpolate_vs_oracle(cuda, case):
+    seed, B, n, m = case
+    unknown = clouds(seed, B, n, "body", dup_frac=0.02)
+    known = clouds(seed + 1, B, m, "body", dup_frac=0.0) if m > n else unknown[:, :m].copy()
+    u, k = _t(unknown, cuda), _t(known, cuda)
+    dist, idx = pu.three_nn(u, k)
+    wd, wi = orc.three_nn(unknown, known)
+    assert np.array_equal(idx.cpu().numpy(), wi)
+    assert np.array_equal(dist.cpu().numpy(), wd)
+    if refgpu.available():
+        rd, ri = refgpu.three_nn(u, k)
+        assert torch.equal(idx, ri) and torch.equal(dist, rd)
+    rs = np.random.RandomState(seed + 2)
+    feats = rs.randn(B, 7, m).astype(np.float32)
+    w = rs.rand(B, n, 3).astype(np.float32)
+    out = pu.three_interpolate(_t(feats, cuda), idx, _t(w, cuda))
+    assert np.array_equal(out.cpu().numpy(), orc.three_interpolate(feats, wi, w))
+    if refgpu.available():
+        assert torch.equal(out, refgpu.three_interpolate(_t(feats, cuda), idx, _t(w, cuda)))
+
+
+def test_backward_ops_vs_oracle(cuda):
+    rs = np.random.RandomState(31)
+    B, C, N, P, S = 2, 6, 500, 64, 8
+    idx = rs.randint(0, N, (B, P, S)).astype(np.int32)
+    feats = torch.from_numpy(rs.randn(B, C, N).astype(np.float32)).to(cuda).requires_grad_(True)
+    go = rs.randn(B, C, P, S).astype(np.float32)
+    out = pu.grouping_operation(feats, _t(idx, cuda))
+    out.backward(_t(go, cuda))
+    np.testing.assert_allclose(feats.grad.cpu().numpy(), orc.grouping_operation_grad(go, idx, N), rtol=1e-5, atol=1e-5)
+    # gather
+    gidx = rs.randint(0, N, (B, P)).astype(np.int32)
+    feats2 = torch.from_numpy(rs.randn(B, C, N).astype(np.float32)).to(cuda).requires_grad_(True)
+    go2 = rs.randn(B, C, P).astype(np.float32)
+    pu.gather_operation(feats2, _t(gidx, cuda)).backward(_t(go2, cuda))
+    np.testing.assert_allclose(feats2.grad.cpu().numpy(), orc.gather_operation_grad(go2, gidx, N), rtol=1e-5, atol=1e-5)
+    # three_interpolate
+    m, n = 40, 300
+    iidx = rs.randint(0, m, (B, n, 3)).astype(np.int32)
+    w = rs.rand(B, n, 3).astype(np.float32)
+    feats3 = torch.from_numpy(rs.randn(B, C, m).astype(np.float32)).to(cuda).requires_grad_(True)
+    go3 = rs.randn(B, C, n).astype(np.float32)
+    pu.three_interpolate(feats3, _t(iidx, cuda), _t(w, cuda)).backward(_t(go3, cuda))
+    np.testing.assert_allclose(feats3.grad.cpu().numpy(), orc.three_interpolate_grad(go3, iidx, w, m), rtol=1e-5, atol=1e-5)
+
+
+def test_query_and_group_backward_matches_composition(cuda):
+    xyz = clouds(41, 2, 600, "cube")
+    x = _t(xyz, cuda)
+    idx, new_xyz = pu.furthest_point_sample_and_gather(x, 50)
+    feats = torch.randn(2, 4, 600, device=cuda)
+    go = torch.randn(2, 7, 50, 16, device=cuda)
+    grads = []
+    for fused in (True, False):
+        xa = x.clone().requires_grad_(True)
+        na = new_xyz.clone().requires_grad_(True)
+        fa = feats.clone().requires_grad_(True)
+        if fused:
+            out = pu.QueryAndGroup(0.2, 16)(xa, na, fa)
+        else:
+            bq = pu.ball_query(0.2, 16, xa, na)
+            gx = pu.grouping_operation(xa.transpose(1, 2).contiguous(), bq) - na.transpose(1, 2).unsqueeze(-1)
+            out = torch.cat([gx, pu.grouping_operation(fa, bq)], dim=1)
+        out.backward(go)
+        grads.append((out.detach(), xa.grad, na.grad, fa.grad))
+    for a, b in zip(*grads):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+
+
+def test_full_size_properties(cuda):
+    """BASELINE full size (N=8192 -> 1024): size-independent properties instead of the (slow) oracle."""
+    B, N, m = 16, 8192, 1024
+    x = _t(clouds(51, B, N, "body"), cuda)
+    idx, new_xyz = pu.furthest_point_sample_and_gather(x, m)
+    i = idx.long()
+    assert int(i[:, 0].abs().max()) == 0
+    # duplicates (exact copies of earlier points) can only be picked once every distinct point is taken: not at m << N
+    d = torch.cdist(new_xyz, new_xyz)
+    d = d + torch.eye(m, device=cuda)[None] * 10
+    assert float(d.min()) > 0, "FPS picked two coincident points"
+    # FPS is greedy: the min-distance-to-chosen-set of each newly chosen point never increases
+    steps = []
+    for b in range(2):
+        dist = torch.full((N,), 1e10, device=cuda)
+        prev = None
+        for j in range(m - 1):
+            dist = torch.minimum(dist, ((x[b] - x[b, i[b, j]]) ** 2).sum(-1))
+            cur = float(dist[i[b, j + 1]])
+            assert abs(cur - float(dist.max())) <= 1e-6 * max(cur, 1e-12) + 1e-12
+            if prev is not None:
+                assert cur <= prev * (1 + 1e-5)
+            prev = cur
+    bq = pu.ball_query(0.1, 32, x, new_xyz)
+    g = torch.gather(x, 1, bq.long().reshape(B, -1, 1).expand(-1, -1, 3)).reshape(B, m, 32, 3)
+    d2 = ((g - new_xyz[:, :, None]) ** 2).sum(-1)
+    assert float(d2.max()) < 0.1 ** 2 * (1 + 1e-5)
+    # ascending index order up to the padding
+    first = bq[:, :, :1]
+    inc = (bq[:, :, 1:] > bq[:, :, :-1]) | (bq[:, :, 1:] == first)
+    assert bool(inc.all())
