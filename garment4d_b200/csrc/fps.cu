@@ -183,7 +183,7 @@ template <int T, int PPT, bool XYZ_REG, bool SIMPLE_KEY>
 static int launch_fps(int b, int n, int m, int lg, const float* xyz, float* temp, int* idx, float* new_xyz, cudaStream_t s) {
     auto kern = fps_kernel<T, PPT, XYZ_REG, SIMPLE_KEY>;
     const size_t smem = (size_t)3 * n * sizeof(float);
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // dynamic + static (the exchange slots) must stay under the 48 KB default
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("fps: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
     }
