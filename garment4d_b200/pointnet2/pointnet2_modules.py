@@ -1,0 +1,217 @@
+"""Set-abstraction / feature-propagation modules with the reference's interface
+(modules/pointnet2/pointnet2/pointnet2_modules.py): same constructor keywords, same sub-module and parameter
+names (``groupers``, ``mlps.{i}.layer{j}.conv.weight`` ...), same ``forward`` signatures and results.
+
+``_PointnetSAModuleBase.forward(xyz, features=None, new_xyz=None) -> (new_xyz, new_features)`` has two routes:
+
+* fused (eval mode, no autograd graph needed through the MLP, max-pool, 3-layer conv+BN+ReLU stacks):
+      g4d_fps_gather  ->  g4d_ball_query2 (both MSG scales from one scan)  ->  per scale g4d_sa_mlp_max
+  (tcgen05 grouped-MLP + max, writes its channel window of the concatenated output directly).  This is the
+  route the reference's posed-garment stage and all inference take: the encoder runs under ``torch.no_grad()``
+  with BatchNorm in eval mode (modules/mesh_encoder.py:416-417, train_temporal.py:227-233).
+* general (training-mode BN / gradients / avg-pool / other MLP depths): the reference's operator sequence,
+  each operator on the B200 kernels (fused QueryAndGroup, then torch conv/bn/relu and pooling).
+"""
+import ctypes
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+from . import pointnet2_utils
+from . import pytorch_utils as pt_utils
+
+
+def _as_point_major_half(features: torch.Tensor) -> torch.Tensor:
+    """(B,C,N) fp32 channel-major -> (B,N,C) fp16 point-major, the gather layout of the fused kernel.
+    A fused SA module attaches this copy to its output as ``_g4d_pm`` so the next level does not recompute it."""
+    pm = getattr(features, "_g4d_pm", None)
+    if pm is not None and pm.shape[0] == features.shape[0] and pm.shape[1] == features.shape[2] and pm.shape[2] == features.shape[1]:
+        return pm
+    return features.detach().transpose(1, 2).to(torch.float16).contiguous()
+
+
+class _FusedBranch:
+    """Device-resident packed parameters of one (grouper, SharedMLP) scale for g4d_sa_mlp_max."""
+
+    def __init__(self, mlp: pt_utils.SharedMLP, nsample: int, c_in: int, device):
+        folded = pt_utils.fold_shared_mlp(mlp)
+        assert folded is not None and len(folded) == 3
+        (w1, b1), (w2, b2), (w3, b3) = [(w.cpu().contiguous(), b.cpu().contiguous()) for w, b in folded]
+        assert w1.shape[1] == c_in + 3
+        L = _lib.lib()
+        self.desc = _lib.SaMlpDesc(c_in, w1.shape[0], w2.shape[0], w3.shape[0], nsample, L.g4d_sa_mlp_k0(c_in))
+        nbytes = L.g4d_sa_mlp_param_bytes(ctypes.byref(self.desc))
+        if nbytes == 0:
+            raise _lib.G4DError("g4d_sa_mlp_param_bytes: " + L.g4d_last_error().decode())
+        blob = torch.empty(nbytes, dtype=torch.uint8)
+        rc = L.g4d_sa_mlp_pack_params(ctypes.byref(self.desc), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                      w3.data_ptr(), b3.data_ptr(), blob.data_ptr())
+        _lib.check(rc, "g4d_sa_mlp_pack_params")
+        self.params = blob.to(device)
+        self.c_out = w3.shape[0]
+
+
+def fused_branch_supported(mlp, grouper, c_in):
+    if not isinstance(grouper, pointnet2_utils.QueryAndGroup) or not grouper.use_xyz:
+        return False
+    if grouper.nsample not in (8, 16, 32, 64, 128) or c_in % 8 != 0 or len(mlp) != 3:
+        return False
+    folded = pt_utils.fold_shared_mlp(mlp)
+    if folded is None:
+        return False
+    c1, c2, c3 = (w.shape[0] for w, _ in folded)
+    return c1 % 16 == 0 and c2 % 16 == 0 and 16 <= c1 <= 256 and 16 <= c2 <= 256 and c3 <= 256
+
+
+class _PointnetSAModuleBase(nn.Module):
+
+    def __init__(self):
+        super().__init__()
+        self.npoint = None
+        self.groupers = None
+        self.mlps = None
+        self.pool_method = 'max_pool'
+        self.fused = True          # set False to force the operator-by-operator route
+        self._fused_cache = {}
+
+    # ---- fused route ------------------------------------------------------------------------------------
+    def _can_fuse(self, xyz, features, new_xyz):
+        if not self.fused or self.training or self.pool_method != 'max_pool' or self.npoint is None:
+            return False
+        if not xyz.is_cuda or xyz.dtype != torch.float32:
+            return False
+        if torch.is_grad_enabled() and (xyz.requires_grad or (features is not None and features.requires_grad)
+                                        or (new_xyz is not None and new_xyz.requires_grad)
+                                        or any(p.requires_grad for p in self.mlps.parameters())):
+            return False
+        c_in = 0 if features is None else features.shape[1]
+        return all(self._branch(i, c_in, xyz.device) is not None for i in range(len(self.groupers)))
+
+    def _branch(self, i, c_in, device):
+        """Packed parameters of scale i (None if that scale cannot take the fused route); rebuilt when any
+        weight / BN statistic changes (load_state_dict, optimizer step, .to())."""
+        key = (i, c_in, str(device))
+        ver = pt_utils.shared_mlp_version(self.mlps[i])
+        hit = self._fused_cache.get(key)
+        if hit is None or hit[0] != ver:
+            br = None
+            if fused_branch_supported(self.mlps[i], self.groupers[i], c_in):
+                br = _FusedBranch(self.mlps[i], self.groupers[i].nsample, c_in, device)
+            hit = (ver, br)
+            self._fused_cache[key] = hit
+        return hit[1]
+
+    def _forward_fused(self, xyz, features, new_xyz):
+        B, N, _ = xyz.shape
+        xyz = xyz.contiguous()
+        if new_xyz is None:
+            _, new_xyz = pointnet2_utils.furthest_point_sample_and_gather(xyz, self.npoint)
+        else:
+            new_xyz = new_xyz.contiguous()
+        P = new_xyz.shape[1]
+        c_in = 0 if features is None else features.shape[1]
+        feat_pm = None if features is None else _as_point_major_half(features)
+        ng = len(self.groupers)
+        if ng == 2:
+            g0, g1 = self.groupers
+            idxs = pointnet2_utils.ball_query_pair(g0.radius, g0.nsample, g1.radius, g1.nsample, xyz, new_xyz)
+        else:
+            idxs = [pointnet2_utils.ball_query(g.radius, g.nsample, xyz, new_xyz) for g in self.groupers]
+        branches = [self._branch(i, c_in, xyz.device) for i in range(ng)]
+        ctot = sum(br.c_out for br in branches)
+        out_cm = torch.empty(B, ctot, P, dtype=torch.float32, device=xyz.device)
+        out_pm = torch.empty(B, P, ctot, dtype=torch.float16, device=xyz.device)
+        L = _lib.lib()
+        off = 0
+        for br, idx in zip(branches, idxs):
+            rc = L.g4d_sa_mlp_max(ctypes.byref(br.desc), _lib.ptr(br.params), B, N, P, _lib.ptr(xyz), _lib.ptr(new_xyz),
+                                  _lib.ptr(idx), _lib.ptr(feat_pm), _lib.ptr(out_cm), _lib.ptr(out_pm), ctot, off,
+                                  _lib.stream_ptr())
+            _lib.check(rc, "g4d_sa_mlp_max")
+            off += br.c_out
+        out_cm._g4d_pm = out_pm
+        return new_xyz, out_cm
+
+    # ---- public forward ----------------------------------------------------------------------------------
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, new_xyz=None) -> (torch.Tensor, torch.Tensor):
+        """xyz (B,N,3), features (B,C,N) or None -> new_xyz (B,npoint,3), new_features (B, sum_k mlps[k][-1], npoint)"""
+        if self._can_fuse(xyz, features, new_xyz):
+            return self._forward_fused(xyz, features, new_xyz)
+
+        new_features_list = []
+        if new_xyz is None and self.npoint is not None:
+            if xyz.requires_grad and torch.is_grad_enabled():
+                # keep the reference graph: gather_operation is differentiable w.r.t. xyz (pointnet2_modules.py:30-35)
+                xyz_flipped = xyz.transpose(1, 2).contiguous()
+                new_xyz = pointnet2_utils.gather_operation(
+                    xyz_flipped, pointnet2_utils.furthest_point_sample(xyz.contiguous(), self.npoint)
+                ).transpose(1, 2).contiguous()
+            else:
+                _, new_xyz = pointnet2_utils.furthest_point_sample_and_gather(xyz.contiguous(), self.npoint)
+        for i in range(len(self.groupers)):
+            new_features = self.groupers[i](xyz, new_xyz, features)       # (B, C, npoint, nsample)
+            new_features = self.mlps[i](new_features)                      # (B, mlp[-1], npoint, nsample)
+            if self.pool_method == 'max_pool':
+                new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+            elif self.pool_method == 'avg_pool':
+                new_features = F.avg_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+            else:
+                raise NotImplementedError
+            new_features_list.append(new_features.squeeze(-1))             # (B, mlp[-1], npoint)
+        return new_xyz, torch.cat(new_features_list, dim=1)
+
+
+class PointnetSAModuleMSG(_PointnetSAModuleBase):
+    """Set abstraction with multi-scale grouping (pointnet2_modules.py:58-91)."""
+
+    def __init__(self, *, npoint: int, radii: List[float], nsamples: List[int], mlps: List[List[int]], bn: bool = True,
+                 use_xyz: bool = True, pool_method='max_pool', instance_norm=False):
+        super().__init__()
+        assert len(radii) == len(nsamples) == len(mlps)
+        self.npoint = npoint
+        self.groupers = nn.ModuleList()
+        self.mlps = nn.ModuleList()
+        for radius, nsample, mlp_spec in zip(radii, nsamples, mlps):
+            self.groupers.append(pointnet2_utils.QueryAndGroup(radius, nsample, use_xyz=use_xyz)
+                                 if npoint is not None else pointnet2_utils.GroupAll(use_xyz))
+            if use_xyz:
+                mlp_spec[0] += 3           # in place, like the reference (callers observe the mutated list)
+            self.mlps.append(pt_utils.SharedMLP(mlp_spec, bn=bn, instance_norm=instance_norm))
+        self.pool_method = pool_method
+
+
+class PointnetSAModule(PointnetSAModuleMSG):
+    """Single-scale set abstraction (pointnet2_modules.py:94-113)."""
+
+    def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None, nsample: int = None,
+                 bn: bool = True, use_xyz: bool = True, pool_method='max_pool', instance_norm=False):
+        super().__init__(mlps=[mlp], npoint=npoint, radii=[radius], nsamples=[nsample], bn=bn, use_xyz=use_xyz,
+                         pool_method=pool_method, instance_norm=instance_norm)
+
+
+class PointnetFPModule(nn.Module):
+    """Feature propagation: 3-NN inverse-distance interpolation + skip concat + SharedMLP (pointnet2_modules.py:116-156)."""
+
+    def __init__(self, *, mlp: List[int], bn: bool = True):
+        super().__init__()
+        self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
+
+    def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
+                known_feats: torch.Tensor) -> torch.Tensor:
+        """unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n), known_feats (B,C2,m) -> (B, mlp[-1], n)"""
+        if known is not None:
+            dist, idx = pointnet2_utils.three_nn(unknown.contiguous(), known.contiguous())
+            dist_recip = 1.0 / (dist + 1e-8)
+            norm = torch.sum(dist_recip, dim=2, keepdim=True)
+            weight = dist_recip / norm
+            interpolated_feats = pointnet2_utils.three_interpolate(known_feats.contiguous(), idx, weight)
+        else:
+            interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+        if unknow_feats is not None:
+            new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
+        else:
+            new_features = interpolated_feats
+        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)

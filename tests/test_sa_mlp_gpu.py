@@ -1,0 +1,98 @@
+"""-m gpu: the tcgen05 grouped-MLP + max kernel and the fused set-abstraction route against a plain PyTorch fp32
+reference of the same op (conv1x1 -> eval BN -> ReLU x3 -> max over the neighbourhood).
+
+Tolerance: operands are fp16 (11-bit significand, the same class as the TF32 cuDNN convolutions the reference
+runs by default), accumulation fp32, relative xyz enters at ~22 bits via a hi/lo split.  We require
+|err| <= 2e-3 * max|ref| + 2e-3 * |ref| per element.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from tests.util import clouds
+
+pytestmark = pytest.mark.gpu
+
+from garment4d_b200.pointnet2 import pointnet2_modules as pm   # noqa: E402
+from garment4d_b200.pointnet2 import pointnet2_utils as pu     # noqa: E402
+
+
+def _randomise_bn(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    for mod in module.modules():
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.weight.data = torch.rand(mod.num_features, generator=g) * 1.5 + 0.25
+            mod.bias.data = torch.randn(mod.num_features, generator=g) * 0.2
+            mod.running_mean = torch.randn(mod.num_features, generator=g) * 0.2
+            mod.running_var = torch.rand(mod.num_features, generator=g) * 1.5 + 0.25
+
+
+def _close(got, ref):
+    err = (got - ref).abs()
+    bound = 2e-3 * ref.abs().max() + 2e-3 * ref.abs()
+    bad = err > bound
+    assert not bool(bad.any()), f"max err {float(err.max()):.3e} (ref max {float(ref.abs().max()):.3e}), {int(bad.sum())} elements out of tolerance"
+
+
+SPECS = [  # (N, npoint, C_in, radii, nsamples, mlps)
+    (1024, 256, 0, [0.1, 0.2], [16, 32], [[0, 16, 16, 32], [0, 32, 32, 64]]),        # SA1-like on a small cloud
+    (1024, 128, 96, [0.2, 0.3], [16, 32], [[96, 32, 32, 64], [96, 64, 64, 128]]),     # SA2
+    (256, 64, 192, [0.3, 0.5], [32, 64], [[192, 64, 64, 128], [192, 128, 128, 256]]), # SA3
+    (500, 50, 16, [0.25], [8], [[16, 16, 32, 48]]),                                   # ragged tile, nsample 8, single scale
+    (300, 30, 8, [0.3], [128], [[8, 32, 16, 200]]),                                   # nsample 128, c3 = 200 (2 blocks, partial)
+]
+
+
+@pytest.mark.parametrize("spec", SPECS, ids=lambda s: f"N{s[0]}c{s[2]}")
+def test_fused_sa_module_vs_torch(cuda, spec):
+    N, npoint, cin, radii, nsamples, mlps = spec
+    torch.manual_seed(0)
+    mod = pm.PointnetSAModuleMSG(npoint=npoint, radii=radii, nsamples=nsamples, mlps=[list(m) for m in mlps], bn=True)
+    _randomise_bn(mod, 1)
+    mod = mod.to(cuda).eval()
+    B = 3
+    xyz = torch.from_numpy(clouds(7, B, N, "body")).to(cuda)
+    feats = torch.randn(B, cin, N, device=cuda) if cin else None
+    with torch.no_grad():
+        new_xyz, out = mod(xyz, feats)                       # fused route
+        assert getattr(out, "_g4d_pm", None) is not None, "fused route was not taken"
+        mod.fused = False
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False              # true fp32 reference
+        try:
+            ref_xyz, ref = mod(xyz, feats)
+        finally:
+            torch.backends.cudnn.allow_tf32 = old
+            mod.fused = True
+    assert torch.equal(new_xyz, ref_xyz)
+    assert out.shape == ref.shape
+    _close(out, ref)
+    _close(out._g4d_pm.float().transpose(1, 2), ref)
+
+
+def test_fused_route_tracks_weight_updates(cuda):
+    torch.manual_seed(1)
+    mod = pm.PointnetSAModule(npoint=32, radius=0.3, nsample=16, mlp=[0, 16, 16, 32]).to(cuda).eval()
+    xyz = torch.from_numpy(clouds(9, 2, 256, "cube")).to(cuda)
+    with torch.no_grad():
+        _, a = mod(xyz)
+        for p in mod.parameters():
+            p.mul_(0.5)
+        _, b = mod(xyz)
+        mod.fused = False
+        _, ref = mod(xyz)
+    assert not torch.allclose(a, b)
+    _close(b, ref)
+
+
+def test_training_mode_uses_operator_route_and_backprops(cuda):
+    torch.manual_seed(2)
+    mod = pm.PointnetSAModuleMSG(npoint=32, radii=[0.3], nsamples=[16], mlps=[[4, 16, 16, 32]]).to(cuda).train()
+    xyz = torch.from_numpy(clouds(9, 2, 256, "cube")).to(cuda)
+    feats = torch.randn(2, 4, 256, device=cuda, requires_grad=True)
+    _, out = mod(xyz, feats)
+    assert getattr(out, "_g4d_pm", None) is None
+    out.sum().backward()
+    assert feats.grad is not None and torch.isfinite(feats.grad).all()
+    assert all(p.grad is not None for p in mod.parameters())
