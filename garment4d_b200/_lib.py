@@ -24,6 +24,7 @@ _SIGNATURES = {
     "g4d_last_error": (ctypes.c_char_p, []),
     "g4d_abi_version": (_i, []),
     "g4d_sm_count": (_i, []),
+    "g4d_launch_count": (ctypes.c_ulonglong, []),
     "g4d_furthest_point_sampling": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "g4d_gather_points": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "g4d_gather_points_grad": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -6,6 +6,9 @@
 namespace g4d {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -31,3 +34,4 @@ int sm_count() {
 G4D_API const char* g4d_last_error(void) { return g4d::g_err; }
 G4D_API int g4d_abi_version(void) { return 1; }
 G4D_API int g4d_sm_count(void) { return g4d::sm_count(); }
+G4D_API unsigned long long g4d_launch_count(void) { return __atomic_load_n(&g4d::g_launches, __ATOMIC_RELAXED); }

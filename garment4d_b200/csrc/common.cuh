@@ -13,7 +13,11 @@ namespace g4d {
 // last error text, readable through g4d_last_error()
 void set_error(const char* fmt, ...);
 
-inline int finish_launch(const char* what) {
+// kernels launched through this library since load (g4d_launch_count); bench.py reports the per-step delta
+void count_launches(int n);
+
+inline int finish_launch(const char* what, int nkernels = 1) {
+    count_launches(nkernels);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) set_error("%s: %s", what, cudaGetErrorString(e));
     return (int)e;

@@ -373,7 +373,7 @@ G4D_API int g4d_lbs(int F, int V, int J, int NB, int betas_rows, int pose2rot, c
         sgemm_acc_kernel<<<grid, 256, 0, s>>>(F, V3, P, pf, P, posedirs, V3, v_posed, V3, 1);
     }
     lbs_rigid_kernel<<<(F + 3) / 4, 128, 0, s>>>(F, J, rot, Jrest, parents, joints, A);
-    int rc = finish_launch("g4d lbs (pose/shape/joints/blend/rigid)");
+    int rc = finish_launch("g4d lbs (pose/shape/joints/blend/rigid)", P > 0 ? 5 : 4);
     if (rc) return rc;
     return launch_skin(F, V, J, 0, v_posed, A, lbs_weights, verts, s);
 }

@@ -33,6 +33,7 @@ extern "C" {
 const char* g4d_last_error(void);       /* text of the calling thread's last failure */
 int g4d_abi_version(void);
 int g4d_sm_count(void);
+unsigned long long g4d_launch_count(void);   /* kernels launched through this library since it was loaded */
 
 /* ---- 1. one-to-one replacements of the reference launchers ------------------------------------- */
 
