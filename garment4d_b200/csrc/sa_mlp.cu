@@ -451,12 +451,13 @@ G4D_API int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int
 
     cudaError_t e = cudaFuncSetAttribute(sa_mlp_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
     if (e != cudaSuccess) { set_error("sa_mlp_max: shared memory opt-in (%u B): %s", a.L.total_smem, cudaGetErrorString(e)); return (int)e; }
-    int occ = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_mlp_max_kernel, SA_THREADS, a.L.total_smem);
-    if (e != cudaSuccess || occ < 1) occ = 1;
-    const int tmem_limit = 512 / (int)a.L.tmem_cols;          // TMEM columns are a per-SM resource too
+    cudaFuncSetAttribute(sa_mlp_max_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    // resident CTAs per SM: shared memory (227 KB usable, 1 KB reserved per CTA), TMEM columns (512 per SM), warps
+    int occ = (int)((227u * 1024u) / (a.L.total_smem + 1024u));
+    const int tmem_limit = 512 / (int)a.L.tmem_cols;
     if (occ > tmem_limit) occ = tmem_limit;
     if (occ > 8) occ = 8;
+    if (occ < 1) occ = 1;
     long long grid = (long long)sm_count() * occ;
     if (grid > a.ntiles) grid = a.ntiles;
     sa_mlp_max_kernel<<<(unsigned)grid, SA_THREADS, a.L.total_smem, (cudaStream_t)stream>>>(a);

@@ -1,0 +1,196 @@
+"""CPU tests (-m "not gpu") of the host side: the C-ABI library loads and exports every symbol the header declares,
+the Python mirror keeps the reference's names / signatures / state-dict keys, parameter folding and packing,
+sharding logic under a world_size-2 gloo group.  No compute call is made (no GPU here)."""
+import ctypes
+import inspect
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "garment4d_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(g4d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from garment4d_b200 import _lib
+    assert os.path.exists(_lib.SO_PATH), "run __graft_entry__.build() first"
+    L = ctypes.CDLL(_lib.SO_PATH)
+    declared = _header_symbols()
+    assert len(declared) >= 25
+    for s in declared:
+        assert hasattr(L, s), f"{s} declared in include/garment4d_b200.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes signature table and header disagree"
+    L.g4d_abi_version.restype = ctypes.c_int
+    assert L.g4d_abi_version() == 1
+
+
+def test_library_is_sm100a_native_and_has_tcgen05():
+    from garment4d_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3g4d17sa_mlp_max_kernelENS_9SaMlpArgsE", _lib.SO_PATH],
+                          capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "LDTM" in sass, "grouped-MLP kernel is not on the tcgen05 path"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from garment4d_b200 import _lib
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "SO_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.G4DError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_pointnet2_cuda_mirror_has_the_reference_surface():
+    import pointnet2_cuda                                 # top-level drop-in name (pointnet2_utils.py:7)
+    want = {  # pointnet2_api.cpp:10-23 with the wrapper argument counts
+        "ball_query_wrapper": 8, "group_points_wrapper": 8, "group_points_grad_wrapper": 8, "gather_points_wrapper": 7,
+        "gather_points_grad_wrapper": 7, "furthest_point_sampling_wrapper": 6, "three_nn_wrapper": 7,
+        "three_interpolate_wrapper": 8, "three_interpolate_grad_wrapper": 8}
+    for name, nargs in want.items():
+        fn = getattr(pointnet2_cuda, name)
+        assert len(inspect.signature(fn).parameters) == nargs
+    # argument order of ball_query: new_xyz before xyz (ball_query.cpp:14-15)
+    assert list(inspect.signature(pointnet2_cuda.ball_query_wrapper).parameters)[5:7] == ["new_xyz_tensor", "xyz_tensor"]
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pointnet2_cuda.ball_query_wrapper(1, 4, 1, 0.1, 2, torch.zeros(1, 1, 3), torch.zeros(1, 4, 3), torch.zeros(1, 1, 2, dtype=torch.int32))
+
+
+def test_operator_and_module_names_match_reference():
+    from garment4d_b200.pointnet2 import pointnet2_modules as pm, pointnet2_utils as pu, pytorch_utils as ptu
+    from garment4d_b200 import lbs
+    for n in ("furthest_point_sample", "gather_operation", "three_nn", "three_interpolate", "grouping_operation", "ball_query",
+              "QueryAndGroup", "GroupAll", "FurthestPointSampling", "GatherOperation", "ThreeNN", "ThreeInterpolate",
+              "GroupingOperation", "BallQuery"):
+        assert hasattr(pu, n)
+    for n in ("PointnetSAModuleMSG", "PointnetSAModule", "PointnetFPModule", "_PointnetSAModuleBase"):
+        assert hasattr(pm, n)
+    for n in ("SharedMLP", "Conv1d", "Conv2d", "FC", "BatchNorm1d", "BatchNorm2d"):
+        assert hasattr(ptu, n)
+    for n in ("lbs", "batch_rodrigues", "batch_rigid_transform", "vertices2joints", "vertices2jointsB", "blend_shapes", "transform_mat"):
+        assert hasattr(lbs, n)
+    assert list(inspect.signature(lbs.lbs).parameters) == ["betas", "pose", "v_template", "shapedirs", "posedirs", "J_regressor",
+                                                           "parents", "lbs_weights", "pose2rot"]
+
+
+def test_encoder_state_dict_keys_match_reference_naming():
+    from garment4d_b200.encoder import Pointnet2MSGSEG
+    m = Pointnet2MSGSEG(input_channels=0, bn=True, global_feat=False)
+    keys = set(m.state_dict().keys())
+    # names from pytorch_utils.py:21-22,83,91,95,108 (checkpoint row)
+    for k in ("SA_modules.0.mlps.1.layer2.conv.weight", "SA_modules.0.mlps.1.layer2.bn.bn.weight",
+              "SA_modules.0.mlps.1.layer2.bn.bn.running_mean", "SA_modules.0.mlps.1.layer2.bn.bn.num_batches_tracked",
+              "SA_modules.2.mlps.1.layer0.conv.weight", "FP_modules.0.mlp.layer0.conv.weight", "FP_modules.2.mlp.layer1.bn.bn.bias",
+              "FC_layer.0.conv.weight", "FC_layer.0.bn.bn.running_var", "FC_layer.2.conv.weight", "FC_layer.2.conv.bias"):
+        assert k in keys, k
+    assert m.state_dict()["SA_modules.2.mlps.1.layer0.conv.weight"].shape == (128, 195, 1, 1)
+    assert not any("conv.bias" in k for k in keys if "SA_modules" in k)     # bias dropped when bn=True (pytorch_utils.py:56)
+    n_params = sum(p.numel() for p in m.parameters())
+    assert n_params == sum(p.numel() for p in Pointnet2MSGSEG(input_channels=0, global_feat=False).parameters())
+    assert Pointnet2MSGSEG(input_channels=0, global_feat=True).Middle_modules is not None
+
+
+def test_fold_shared_mlp_equals_conv_bn_relu_on_cpu():
+    from garment4d_b200.pointnet2 import pytorch_utils as ptu
+    torch.manual_seed(0)
+    mlp = ptu.SharedMLP([7, 16, 32, 24], bn=True).eval()
+    for mod in mlp.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(); mod.running_var.uniform_(0.5, 2); mod.weight.data.uniform_(0.5, 2); mod.bias.data.normal_()
+    x = torch.randn(2, 7, 5, 3)
+    with torch.no_grad():
+        ref = mlp(x.clone())
+        y = x
+        for w, b in ptu.fold_shared_mlp(mlp):
+            y = torch.relu(torch.einsum("oc,bcpk->bopk", w, y) + b[None, :, None, None])
+    assert torch.allclose(y, ref, atol=1e-5, rtol=1e-5)
+    v0 = ptu.shared_mlp_version(mlp)
+    with torch.no_grad():
+        mlp[0][0].weight.mul_(2)          # optimizer steps / load_state_dict bump the version counter the same way
+    assert ptu.shared_mlp_version(mlp) != v0
+    assert ptu.fold_shared_mlp(ptu.SharedMLP([4, 8], bn=True, preact=True, first=False)) is None     # pre-activation order: not foldable
+
+
+def test_sa_mlp_param_packing_layout():
+    """g4d_sa_mlp_pack_params (host function, no GPU): UMMA canonical K-major image + hi/lo split of the xyz columns."""
+    from garment4d_b200 import _lib
+    L = _lib.lib()
+    c_in, c1, c2, c3, K = 16, 32, 16, 40, 16
+    d = _lib.SaMlpDesc(c_in, c1, c2, c3, K, L.g4d_sa_mlp_k0(c_in))
+    assert d.k0 == 32
+    nbytes = L.g4d_sa_mlp_param_bytes(ctypes.byref(d))
+    c3p = 128
+    assert nbytes == 2 * (d.k0 * c1 + c1 * c2 + c2 * c3p) + 4 * (c1 + c2 + c3p)
+    rs = np.random.RandomState(0)
+    w1, w2, w3 = (rs.randn(c1, 3 + c_in).astype(np.float32), rs.randn(c2, c1).astype(np.float32), rs.randn(c3, c2).astype(np.float32))
+    b1, b2, b3 = (rs.randn(c).astype(np.float32) for c in (c1, c2, c3))
+    blob = np.zeros(nbytes, np.uint8)
+    rc = L.g4d_sa_mlp_pack_params(ctypes.byref(d), *(a.ctypes.data for a in (w1, b1, w2, b2, w3, b3)), blob.ctypes.data)
+    assert rc == 0
+    W1 = blob[:2 * d.k0 * c1].view(np.float16).reshape(d.k0 // 8, c1, 8)          # [k/8][row][k%8]
+    W1 = W1.transpose(1, 0, 2).reshape(c1, d.k0).astype(np.float32)                 # (row, k)
+    assert np.array_equal(W1[:, :c_in], w1[:, 3:].astype(np.float16).astype(np.float32))       # features first
+    wh = w1[:, :3].astype(np.float16).astype(np.float32)
+    assert np.array_equal(W1[:, c_in:c_in + 3], wh) and np.array_equal(W1[:, c_in + 3:c_in + 6], wh)
+    assert np.allclose(W1[:, c_in + 6:c_in + 9], w1[:, :3] - wh, atol=1e-6)
+    assert np.abs(W1[:, c_in:c_in + 3] + W1[:, c_in + 6:c_in + 9] - w1[:, :3]).max() < 2e-6     # hi + lo recovers fp32 weights
+    assert not W1[:, c_in + 9:].any()
+    off = 2 * (d.k0 * c1 + c1 * c2 + c2 * c3p)
+    assert np.array_equal(blob[off:off + 4 * c1].view(np.float32), b1)
+    bad = _lib.SaMlpDesc(c_in, 20, c2, c3, K, d.k0)
+    assert L.g4d_sa_mlp_param_bytes(ctypes.byref(bad)) == 0 and b"multiples of 16" in L.g4d_last_error()
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-clouds", "1", "--config", "c2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+
+
+# ---- multi-process sharding (world_size 2, gloo) -------------------------------------------------------------
+
+_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, os.environ["G4D_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from garment4d_b200.sharding import shard_sequences, max_over_ranks
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+lo, hi = shard_sequences(7, r, w)
+t = max_over_ranks(float(10 + r))
+own = torch.zeros(7, dtype=torch.int64); own[lo:hi] = 1
+dist.all_reduce(own)
+if r == 0:
+    print(json.dumps({"cover": own.tolist(), "tmax": t, "lo_hi": [lo, hi]}))
+dist.destroy_process_group()
+'''
+
+
+def test_sharding_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, G4D_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29731", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    import json
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["cover"] == [1] * 7            # every sequence owned by exactly one rank
+    assert res["tmax"] == 11.0                # max over ranks, as bench.py reports
+    assert res["lo_hi"] == [0, 4]
