@@ -19,6 +19,11 @@ class SaMlpDesc(ctypes.Structure):
     _fields_ = [("c_in", _i), ("c1", _i), ("c2", _i), ("c3", _i), ("nsample", _i), ("k0", _i)]
 
 
+class FpDesc(ctypes.Structure):
+    """struct g4d_fp_desc"""
+    _fields_ = [("c_in", _i), ("c1", _i), ("c2", _i), ("h1", _i), ("h2", _i)]
+
+
 _SIGNATURES = {
     # name: (restype, argtypes)
     "g4d_last_error": (ctypes.c_char_p, []),
@@ -37,10 +42,17 @@ _SIGNATURES = {
     "g4d_fps_gather": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4d_ball_query2": (_i, [_i, _i, _i, _f, _i, _vp, _f, _i, _vp, _vp, _vp, _vp]),
     "g4d_query_and_group": (_i, [_i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_grid_bytes": (_sz, [_i, _i]),
+    "g4d_grid_build": (_i, [_i, _i, _vp, _f, _vp, _vp]),
+    "g4d_ball_query2_grid": (_i, [_i, _i, _i, _f, _i, _vp, _f, _i, _vp, _vp, _vp, _vp]),
+    "g4d_three_nn_grid": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_sa_mlp_k0": (_i, [_i]),
     "g4d_sa_mlp_param_bytes": (_sz, [ctypes.POINTER(SaMlpDesc)]),
     "g4d_sa_mlp_pack_params": (_i, [ctypes.POINTER(SaMlpDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_sa_mlp_max": (_i, [ctypes.POINTER(SaMlpDesc), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "g4d_fp_param_bytes": (_sz, [ctypes.POINTER(FpDesc)]),
+    "g4d_fp_pack_params": (_i, [ctypes.POINTER(FpDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_fp_interp_mlp": (_i, [ctypes.POINTER(FpDesc), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_batch_rodrigues": (_i, [_i, _vp, _vp, _vp]),
     "g4d_vertices2joints": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "g4d_batch_rigid_transform": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

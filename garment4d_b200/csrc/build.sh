@@ -10,7 +10,7 @@ mkdir -p "$HERE/obj"
 pids=()
 for f in "$HERE"/*.cu; do
     o="$HERE/obj/$(basename "${f%.cu}").o"
-    if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "${1:-}" = "--force" ]; then
+    if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/umma.cuh" -nt "$o" ] || [ "${1:-}" = "--force" ]; then
         ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; exit 1; } ) &
         pids+=($!)
     fi

@@ -1,0 +1,334 @@
+// Uniform-grid acceleration of the two neighbour searches of the hot path, with results IDENTICAL to the
+// brute-force reference kernels (ball_query_gpu.cu:9-45, interpolate_gpu.cu:9-52):
+//
+//   g4d_grid_build          per cloud: bounding box -> cell size >= the search radius -> counting sort of the points
+//                           by cell (one CTA per cloud, histogram and cursors in shared memory)
+//   g4d_ball_query2_grid    one warp per query visits the 27 neighbouring cells (9 contiguous runs of the sorted
+//                           array), tests candidates with the reference's exact distance arithmetic and sets bit k
+//                           of a per-warp N-bit bitmap for every hit; the first nsample set bits ARE "the first
+//                           nsample hits in ascending index order" -> extracted with popcount prefix sums, padded
+//                           with the lowest set bit.  Both MSG radii share one candidate walk (two bitmaps).
+//   g4d_three_nn_grid       one thread per unknown point walks shells of cells of a grid over the KNOWN points and
+//                           keeps the 3 best under the total order (d, k) -- exactly what the reference's strict '<'
+//                           insertion in ascending k produces -- until the shell's distance bound exceeds the third
+//                           best (conservative margin, so rounding can never end the search early).
+//
+// Work drops from N*P (8192*1024 per cloud at SA1) distance tests to ~a few hundred per query.
+#include <float.h>
+#include "common.cuh"
+
+namespace g4d {
+
+constexpr int GRID_MAX_CELLS = 4096;
+constexpr int GRID_HDR = 16;                 // 4-byte words
+// per-cloud grid record: [hdr 16 words][cell_start GRID_MAX_CELLS+1 ints][pad to 16 B][sorted float4 n]
+struct GridHdr {
+    float ox, oy, oz, inv_h;
+    int dx, dy, dz, ncells;
+    float h;
+    int pad[7];
+};
+static_assert(sizeof(GridHdr) == GRID_HDR * 4, "GridHdr layout");
+
+__host__ __device__ inline size_t grid_cloud_words(int n) {
+    size_t w = GRID_HDR + (GRID_MAX_CELLS + 1);
+    w = (w + 3) / 4 * 4;
+    return w + (size_t)n * 4;
+}
+__device__ __forceinline__ const GridHdr* grid_hdr(const float* g) { return reinterpret_cast<const GridHdr*>(g); }
+__device__ __forceinline__ const int* grid_cell_start(const float* g) { return reinterpret_cast<const int*>(g) + GRID_HDR; }
+__device__ __forceinline__ const float4* grid_sorted(const float* g) {
+    return reinterpret_cast<const float4*>(g + (GRID_HDR + GRID_MAX_CELLS + 1 + 3) / 4 * 4);
+}
+
+__device__ __forceinline__ int cell_coord(float v, float o, float inv_h, int dim) {
+    const int c = __float2int_rd(__fmul_rn(__fsub_rn(v, o), inv_h));     // NaN -> 0
+    return min(max(c, 0), dim - 1);
+}
+
+constexpr int GB_THREADS = 512;
+
+__global__ void __launch_bounds__(GB_THREADS)
+grid_build_kernel(int n, const float* __restrict__ xyz_all, float min_cell, float* __restrict__ grid_all) {
+    __shared__ int hist[GRID_MAX_CELLS];
+    __shared__ float red[6][GB_THREADS / 32];
+    __shared__ GridHdr hdr;
+    __shared__ int warp_tot[GB_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* xyz = xyz_all + (size_t)blockIdx.x * n * 3;
+    float* g = grid_all + (size_t)blockIdx.x * grid_cloud_words(n);
+
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int k = tid; k < n; k += GB_THREADS)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = __ldg(xyz + 3 * k + a); lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
+        }
+        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+    }
+    for (int c = tid; c < GRID_MAX_CELLS; c += GB_THREADS) hist[c] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        float L[3], H[3];
+        for (int a = 0; a < 3; ++a) {
+            L[a] = red[a][0]; H[a] = red[3 + a][0];
+            for (int w = 1; w < GB_THREADS / 32; ++w) { L[a] = fminf(L[a], red[a][w]); H[a] = fmaxf(H[a], red[3 + a][w]); }
+        }
+        // cell edge strictly larger than the search radius, so |x - q| < r always lands within +-1 cell even after rounding
+        const float ex = H[0] - L[0], ey = H[1] - L[1], ez = H[2] - L[2];
+        // min_cell < 0: automatic, -min_cell cells along the longest axis (used when no search radius is implied)
+        float h = min_cell > 0.f ? min_cell * 1.0001f : fmaxf(fmaxf(ex, ey), ez) / -min_cell;
+        if (!(h > 1e-30f)) h = 1e-30f;
+        int dx = 1, dy = 1, dz = 1;
+        const bool sane = isfinite(ex) && isfinite(ey) && isfinite(ez) && h > 0.f && isfinite(h) && ex >= 0.f && ey >= 0.f && ez >= 0.f;
+        if (sane) {
+            for (int it = 0; it < 200; ++it) {
+                const float fx = floorf(ex / h) + 1.f, fy = floorf(ey / h) + 1.f, fz = floorf(ez / h) + 1.f;
+                if (fx * fy * fz <= (float)GRID_MAX_CELLS) { dx = (int)fx; dy = (int)fy; dz = (int)fz; break; }
+                h *= 1.25f;
+                if (it == 199) { dx = dy = dz = 1; }
+            }
+        }
+        hdr.ox = sane ? L[0] : 0.f; hdr.oy = sane ? L[1] : 0.f; hdr.oz = sane ? L[2] : 0.f;
+        hdr.h = h; hdr.inv_h = (dx * dy * dz > 1) ? 1.0f / h : 0.f;
+        hdr.dx = dx; hdr.dy = dy; hdr.dz = dz; hdr.ncells = dx * dy * dz;
+        for (int i = 0; i < 7; ++i) hdr.pad[i] = 0;
+        *reinterpret_cast<GridHdr*>(g) = hdr;
+    }
+    __syncthreads();
+    const GridHdr H = hdr;
+    for (int k = tid; k < n; k += GB_THREADS) {
+        const int c = (cell_coord(__ldg(xyz + 3 * k + 2), H.oz, H.inv_h, H.dz) * H.dy + cell_coord(__ldg(xyz + 3 * k + 1), H.oy, H.inv_h, H.dy)) * H.dx +
+                      cell_coord(__ldg(xyz + 3 * k), H.ox, H.inv_h, H.dx);
+        atomicAdd(&hist[c], 1);
+    }
+    __syncthreads();
+    // exclusive scan of hist[0..GRID_MAX_CELLS): 8 cells per thread
+    constexpr int CPT = GRID_MAX_CELLS / GB_THREADS;
+    int local[CPT], sum = 0;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { local[i] = hist[tid * CPT + i]; sum += local[i]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    int run = base + incl - sum;
+    int* cell_start = reinterpret_cast<int*>(g) + GRID_HDR;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { hist[tid * CPT + i] = run; cell_start[tid * CPT + i] = run; run += local[i]; }
+    if (tid == GB_THREADS - 1) cell_start[GRID_MAX_CELLS] = run;
+    __syncthreads();
+    float4* sorted = reinterpret_cast<float4*>(g + (GRID_HDR + GRID_MAX_CELLS + 1 + 3) / 4 * 4);
+    for (int k = tid; k < n; k += GB_THREADS) {
+        const float x = __ldg(xyz + 3 * k), y = __ldg(xyz + 3 * k + 1), z = __ldg(xyz + 3 * k + 2);
+        const int c = (cell_coord(z, H.oz, H.inv_h, H.dz) * H.dy + cell_coord(y, H.oy, H.inv_h, H.dy)) * H.dx + cell_coord(x, H.ox, H.inv_h, H.dx);
+        const int pos = atomicAdd(&hist[c], 1);
+        sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BQG_WARPS = 8;
+constexpr int BQG_QPW = 4;
+
+template <int NS>
+__global__ void __launch_bounds__(BQG_WARPS * 32)
+ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_xyz_all, const float* __restrict__ grid_all,
+                       float r2_0, int K0, int* __restrict__ idx0_all, float r2_1, int K1, int* __restrict__ idx1_all) {
+    extern __shared__ unsigned bitmap_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t cloud = blockIdx.y;
+    const float* g = grid_all + cloud * grid_cloud_words(n);
+    const GridHdr H = *grid_hdr(g);
+    const int* cell_start = grid_cell_start(g);
+    const float4* sorted = grid_sorted(g);
+    unsigned* bm[2];
+    bm[0] = bitmap_all + (size_t)warp * NS * nwords;
+    bm[1] = bm[0] + nwords;
+    for (int s = 0; s < NS; ++s)
+        for (int w = lane; w < nwords; w += 32) bm[s][w] = 0u;
+    __syncwarp();
+    const float r2[2] = {r2_0, r2_1};
+    const int KK[2] = {K0, K1};
+    int* outs[2] = {idx0_all + cloud * (size_t)m * K0, NS > 1 ? idx1_all + cloud * (size_t)m * K1 : nullptr};
+    const int wpl = (nwords + 31) / 32;      // bitmap words per lane (consecutive)
+
+    for (int qi = 0; qi < BQG_QPW; ++qi) {
+        const int q = (blockIdx.x * BQG_WARPS + warp) * BQG_QPW + qi;
+        if (q >= m) break;                  // warp-uniform
+        const float* qp = new_xyz_all + (cloud * m + q) * 3;
+        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        const int cx = cell_coord(qx, H.ox, H.inv_h, H.dx), cy = cell_coord(qy, H.oy, H.inv_h, H.dy), cz = cell_coord(qz, H.oz, H.inv_h, H.dz);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, H.dx - 1);
+        for (int zz = max(cz - 1, 0); zz <= min(cz + 1, H.dz - 1); ++zz)
+            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, H.dy - 1); ++yy) {
+                const int row = (zz * H.dy + yy) * H.dx;
+                const int beg = __ldg(cell_start + row + x0), end = __ldg(cell_start + row + x1 + 1);
+                for (int j = beg + lane; j < end; j += 32) {
+                    const float4 p = __ldg(sorted + j);
+                    const float d2 = sqdist_ref(qx - p.x, qy - p.y, qz - p.z);
+                    const unsigned k = (unsigned)__float_as_int(p.w);
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+                        if (d2 < r2[s]) atomicOr(&bm[s][k >> 5], 1u << (k & 31));
+                }
+            }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int K = KK[s];
+            int* row = outs[s] + (size_t)q * K;
+            // each lane owns wpl consecutive words; exclusive prefix of popcounts across lanes
+            int cnt = 0;
+            for (int w = 0; w < wpl; ++w) { const int wi = lane * wpl + w; if (wi < nwords) cnt += __popc(bm[s][wi]); }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (total > 0) {       // rows without any hit are left untouched (ball_query_gpu.cu: idx stays as the caller zero-filled it)
+                int rank = incl - cnt;
+                int first_local = 0x7FFFFFFF;
+                for (int w = 0; w < wpl; ++w) {
+                    const int wi = lane * wpl + w;
+                    if (wi >= nwords) break;
+                    unsigned bits = bm[s][wi];
+                    if (bits && first_local == 0x7FFFFFFF) first_local = wi * 32 + __ffs(bits) - 1;
+                    while (bits && rank < K) {
+                        const int b = __ffs(bits) - 1;
+                        row[rank++] = wi * 32 + b;
+                        bits &= bits - 1;
+                    }
+                }
+                const int first = __reduce_min_sync(0xFFFFFFFFu, first_local);
+                for (int p = total + lane; p < K; p += 32) row[p] = first;
+            }
+            for (int w = 0; w < wpl; ++w) { const int wi = lane * wpl + w; if (wi < nwords) bm[s][wi] = 0u; }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// three nearest neighbours through a grid over the KNOWN points.  order (optional): processing order of the
+// unknown points (the 'k' column of a grid built over them) so that the threads of a warp are spatial neighbours.
+
+__device__ __forceinline__ void nn3_insert(float d, int k, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
+    // total order (d, k): identical to the reference's strict '<' insertion while scanning k upwards
+    if (d < b1 || (d == b1 && k < i1)) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+    else if (d < b2 || (d == b2 && k < i2)) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+    else if (d < b3 || (d == b3 && k < i3)) { b3 = d; i3 = k; }
+}
+
+__global__ void __launch_bounds__(256)
+three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const float* __restrict__ kgrid_all,
+                     const float* __restrict__ ugrid_all, float* __restrict__ dist2_all, int* __restrict__ idx_all) {
+    const size_t cloud = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int pt = t;
+    if (ugrid_all) pt = __float_as_int(__ldg(&grid_sorted(ugrid_all + cloud * grid_cloud_words(n))[t].w));
+    const float* g = kgrid_all + cloud * grid_cloud_words(m);
+    const GridHdr H = *grid_hdr(g);
+    const int* cell_start = grid_cell_start(g);
+    const float4* sorted = grid_sorted(g);
+    const float* u = unknown_all + (cloud * n + pt) * 3;
+    const float ux = __ldg(u), uy = __ldg(u + 1), uz = __ldg(u + 2);
+    const int cx = cell_coord(ux, H.ox, H.inv_h, H.dx), cy = cell_coord(uy, H.oy, H.inv_h, H.dy), cz = cell_coord(uz, H.oz, H.inv_h, H.dz);
+    float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+    int i1 = 0, i2 = 0, i3 = 0;
+    // when fewer than 3 candidates exist the reference leaves index 0 / distance 1e40 -> inf: (inf, 0) entries; a real
+    // candidate with k = 0 and finite d always beats them, and d == inf candidates never insert in the reference either.
+    const int maxring = max(max(max(cx, H.dx - 1 - cx), max(cy, H.dy - 1 - cy)), max(cz, H.dz - 1 - cz));
+    for (int R = 0; R <= maxring; ++R) {
+        for (int zz = max(cz - R, 0); zz <= min(cz + R, H.dz - 1); ++zz) {
+            const bool zshell = (zz == cz - R) || (zz == cz + R);
+            for (int yy = max(cy - R, 0); yy <= min(cy + R, H.dy - 1); ++yy) {
+                const bool full = zshell || (yy == cy - R) || (yy == cy + R);
+                const int row = (zz * H.dy + yy) * H.dx;
+                // full row of the shell: one contiguous run; otherwise only the two end cells x = cx-R and x = cx+R
+                const int nseg = full ? 1 : 2;
+                for (int sgm = 0; sgm < nseg; ++sgm) {
+                    int xa, xb;
+                    if (full) { xa = max(cx - R, 0); xb = min(cx + R, H.dx - 1); }
+                    else { xa = xb = (sgm == 0 ? cx - R : cx + R); if (xa < 0 || xa >= H.dx || (sgm == 1 && R == 0)) continue; }
+                    const int beg = __ldg(cell_start + row + xa), end = __ldg(cell_start + row + xb + 1);
+                    for (int j = beg; j < end; ++j) {
+                        const float4 p = __ldg(sorted + j);
+                        const float d = sqdist_ref(ux - p.x, uy - p.y, uz - p.z);
+                        if (d < b3 || (d == b3 && __float_as_int(p.w) < i3)) nn3_insert(d, __float_as_int(p.w), b1, b2, b3, i1, i2, i3);
+                    }
+                }
+            }
+        }
+        // every unvisited known point is at least R*h away along some axis; 0.998 keeps the test conservative under rounding
+        const float bound = (float)R * H.h;
+        if (b3 < bound * bound * 0.998f) break;
+    }
+    float* od = dist2_all + (cloud * n + pt) * 3;
+    int* oi = idx_all + (cloud * n + pt) * 3;
+    od[0] = b1; od[1] = b2; od[2] = b3;
+    oi[0] = i1; oi[1] = i2; oi[2] = i3;
+}
+
+}  // namespace g4d
+
+using namespace g4d;
+
+G4D_API size_t g4d_grid_bytes(int b, int n) { return (size_t)(b < 0 ? 0 : b) * grid_cloud_words(n < 0 ? 0 : n) * 4; }
+
+// Builds one grid per cloud over xyz (b,n,3) with cell edge >= min_cell (grown until <= 4096 cells).  grid: device buffer of
+// g4d_grid_bytes(b,n), 16-byte aligned.
+G4D_API int g4d_grid_build(int b, int n, const float* xyz, float min_cell, void* grid, void* stream) {
+    if (b < 0 || n < 0) return bad_arg("grid_build: negative size");
+    if (b == 0) return 0;
+    if (!xyz || !grid || ((uintptr_t)grid & 15)) return bad_arg("grid_build: null or misaligned pointer");
+    if (!(min_cell > 0.f) && !(min_cell <= -1.f)) return bad_arg("grid_build: min_cell must be positive, or <= -1 for 'that many cells along the longest axis'");
+    grid_build_kernel<<<b, GB_THREADS, 0, (cudaStream_t)stream>>>(n, xyz, min_cell, (float*)grid);
+    return finish_launch("g4d grid_build");
+}
+
+// Same results as g4d_ball_query2 / g4d_ball_query (idx1 = NULL: one scale).  grid: g4d_grid_build over xyz with
+// min_cell >= max(radius0, radius1).  n <= 65536.
+G4D_API int g4d_ball_query2_grid(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
+                                 const float* new_xyz, const void* grid, void* stream) {
+    if (b < 0 || n < 0 || m < 0 || nsample0 <= 0 || (idx1 && nsample1 <= 0)) return bad_arg("ball_query2_grid: bad size");
+    if (b == 0 || m == 0 || n == 0) return 0;
+    if (!new_xyz || !grid || !idx0) return bad_arg("ball_query2_grid: null pointer");
+    if (n > 65536) return bad_arg("ball_query2_grid: n > 65536 (use g4d_ball_query2)");
+    const int nwords = (n + 31) / 32;
+    const int ns = idx1 ? 2 : 1;
+    const size_t smem = (size_t)BQG_WARPS * ns * nwords * 4;
+    dim3 gridDim((m + BQG_WARPS * BQG_QPW - 1) / (BQG_WARPS * BQG_QPW), b);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ns == 2) {
+        if (smem > 32 * 1024) cudaFuncSetAttribute(ball_query_grid_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ball_query_grid_kernel<2><<<gridDim, BQG_WARPS * 32, smem, s>>>(n, m, nwords, new_xyz, (const float*)grid, radius0 * radius0, nsample0,
+                                                                        idx0, radius1 * radius1, nsample1, idx1);
+    } else {
+        if (smem > 32 * 1024) cudaFuncSetAttribute(ball_query_grid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ball_query_grid_kernel<1><<<gridDim, BQG_WARPS * 32, smem, s>>>(n, m, nwords, new_xyz, (const float*)grid, radius0 * radius0, nsample0,
+                                                                        idx0, 0.f, 1, nullptr);
+    }
+    return finish_launch("g4d ball_query2_grid");
+}
+
+// Same results as g4d_three_nn.  known_grid: g4d_grid_build over the KNOWN points (b,m,3) (any positive min_cell; a good
+// choice is the typical neighbour spacing).  unknown_grid (optional): a grid over the unknown points, used only as a
+// spatially coherent processing order.
+G4D_API int g4d_three_nn_grid(int b, int n, int m, const float* unknown, const void* known_grid, const void* unknown_grid,
+                              float* dist2, int* idx, void* stream) {
+    if (b < 0 || n < 0 || m < 0) return bad_arg("three_nn_grid: negative size");
+    if (b == 0 || n == 0) return 0;
+    if (!unknown || !known_grid || !dist2 || !idx) return bad_arg("three_nn_grid: null pointer");
+    dim3 gridDim((n + 255) / 256, b);
+    three_nn_grid_kernel<<<gridDim, 256, 0, (cudaStream_t)stream>>>(n, m, unknown, (const float*)known_grid, (const float*)unknown_grid, dist2, idx);
+    return finish_launch("g4d three_nn_grid");
+}

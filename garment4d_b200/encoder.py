@@ -7,9 +7,13 @@ The reference file cannot be imported on its own (it pulls ``utils.config`` -- a
 ``utils.dataloader``), so the 7 segmentation classes (utils/dataloader.py:24) are a constructor default here.
 Garment4D builds it as ``Pointnet2MSGSEG(input_channels=0, bn=True, global_feat=False)`` (modules/mesh_encoder.py:49).
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 
+from . import _lib
+from .pointnet2 import pointnet2_cuda_bridge as _bridge
 from .pointnet2 import pytorch_utils as pt_utils
 from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModule, PointnetSAModuleMSG
 
@@ -60,12 +64,38 @@ class Pointnet2MSGSEG(nn.Module):
             l_features.append(li_features)
         return l_xyz, l_features
 
+    fused = True      # set False to force the module-by-module route for the finest FP level + head
+
+    def _fused_fp0_head(self, l_xyz, l_features):
+        """Finest feature-propagation level + FC head in one tcgen05 kernel (eval mode, no autograd, no skip features):
+        three_nn -> g4d_fp_interp_mlp.  Returns (l_features[0], sem_logits) or None when the route does not apply."""
+        fp = self.FP_modules[0]
+        if (not self.fused or self.training or l_features[0] is not None or not l_xyz[0].is_cuda
+                or (torch.is_grad_enabled() and (l_features[1].requires_grad or any(p.requires_grad for p in self.parameters())))):
+            return None
+        ver = pt_utils.shared_mlp_version(fp.mlp) + pt_utils.shared_mlp_version(self.FC_layer)
+        key = str(l_xyz[0].device)
+        hit = getattr(self, "_fp0_cache", {}).get(key)
+        if hit is None or hit[0] != ver:
+            packed = _bridge.pack_fp_head(fp.mlp, self.FC_layer, l_xyz[0].device)
+            self._fp0_cache = {key: (ver, packed)}
+            hit = self._fp0_cache[key]
+        if hit[1] is None:
+            return None
+        return _bridge.fp_interp_mlp(hit[1], l_xyz[0], l_xyz[1], l_features[1])
+
     def forward(self, pointcloud: torch.Tensor):
         """pointcloud (B, N, 3 + input_channels) -> (middle_features | None, sem_logits (B,N,class_num),
         l_features [4], l_xyz [4])  (pointnet2encoder.py:112-145)"""
         l_xyz, l_features = self.sa_stack(pointcloud)
         middle_features = self.Middle_modules(l_xyz[-1], l_features[-1])[1] if self.global_feat else None
-        for i in range(-1, -(len(self.FP_modules) + 1), -1):
+        nfp = len(self.FP_modules)
+        for i in range(-1, -nfp, -1):
             l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
-        sem_logits = self.FC_layer(l_features[0]).transpose(1, 2).contiguous()
+        fused = self._fused_fp0_head(l_xyz, l_features)
+        if fused is not None:
+            l_features[0], sem_logits = fused
+        else:
+            l_features[0] = self.FP_modules[0](l_xyz[0], l_xyz[1], l_features[0], l_features[1])
+            sem_logits = self.FC_layer(l_features[0]).transpose(1, 2).contiguous()
         return middle_features, sem_logits, l_features, l_xyz

@@ -34,6 +34,34 @@ def _f32(*shape, device):
     return torch.empty(*shape, dtype=torch.float32, device=device)
 
 
+GRID_MIN_POINTS = 2048     # below this the brute-force scans are already cheap
+
+
+def build_grid(xyz: torch.Tensor, min_cell: float) -> torch.Tensor:
+    """Cell-sorted copy of every cloud (g4d_grid_build).  min_cell > 0: cell edge >= min_cell; min_cell <= -1: that many
+    cells along the longest axis.  The grid is remembered on the tensor (``xyz._g4d_grid``) for later searches."""
+    assert xyz.is_contiguous() and xyz.is_cuda and xyz.dtype == torch.float32
+    B, N, _ = xyz.shape
+    L = _lib.lib()
+    grid = torch.empty(L.g4d_grid_bytes(B, N) // 4, dtype=torch.float32, device=xyz.device)
+    _lib.check(L.g4d_grid_build(B, N, _lib.ptr(xyz), float(min_cell), _lib.ptr(grid), _lib.stream_ptr()), "g4d_grid_build")
+    try:
+        xyz._g4d_grid = (grid, float(min_cell), xyz._version)
+    except Exception:
+        pass
+    return grid
+
+
+def _cached_grid(xyz, need_cell=None):
+    """A grid previously built over this very tensor (same version counter); need_cell: minimum cell edge required."""
+    hit = getattr(xyz, "_g4d_grid", None)
+    if hit is None or hit[2] != xyz._version:
+        return None
+    if need_cell is not None and not (hit[1] >= need_cell):
+        return None
+    return hit[0]
+
+
 class FurthestPointSampling(Function):
     @staticmethod
     def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
@@ -104,7 +132,7 @@ class ThreeNN(Function):
         m = known.size(1)
         dist2 = _f32(B, N, 3, device=unknown.device)
         idx = _i32(B, N, 3, device=unknown.device)
-        pointnet2.three_nn_wrapper(B, N, m, unknown, known, dist2, idx)
+        three_nn_raw(unknown, known, dist2, idx)
         ctx.mark_non_differentiable(idx)
         return torch.sqrt(dist2), idx
 
@@ -114,6 +142,21 @@ class ThreeNN(Function):
 
 
 three_nn = ThreeNN.apply
+
+
+def three_nn_raw(unknown, known, dist2, idx):
+    """Fills dist2 (SQUARED distances) and idx like the reference kernel; large problems go through the uniform grid
+    (identical results), small ones through the 1:1 replacement of three_nn_kernel_fast."""
+    B, N, _ = unknown.size()
+    m = known.size(1)
+    if N >= GRID_MIN_POINTS and 512 <= m <= (1 << 20):
+        kgrid = build_grid(known, -max(4.0, round(float(m) ** 0.5 / 2)))
+        ugrid = _cached_grid(unknown)      # only a processing order: any grid over `unknown` will do
+        rc = _lib.lib().g4d_three_nn_grid(B, N, m, _lib.ptr(unknown), _lib.ptr(kgrid), _lib.ptr(ugrid), _lib.ptr(dist2),
+                                          _lib.ptr(idx), _lib.stream_ptr())
+        _lib.check(rc, "g4d_three_nn_grid")
+    else:
+        pointnet2.three_nn_wrapper(B, N, m, unknown, known, dist2, idx)
 
 
 class ThreeInterpolate(Function):
@@ -176,7 +219,15 @@ class BallQuery(Function):
         B, N, _ = xyz.size()
         npoint = new_xyz.size(1)
         idx = torch.zeros(B, npoint, nsample, dtype=torch.int32, device=xyz.device)
-        pointnet2.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
+        if GRID_MIN_POINTS <= N <= 65536:
+            grid = _cached_grid(xyz, radius)
+            if grid is None:
+                grid = build_grid(xyz, radius)
+            rc = _lib.lib().g4d_ball_query2_grid(B, N, npoint, float(radius), nsample, _lib.ptr(idx), 0.0, 0, None,
+                                                 _lib.ptr(new_xyz), _lib.ptr(grid), _lib.stream_ptr())
+            _lib.check(rc, "g4d_ball_query2_grid")
+        else:
+            pointnet2.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
         ctx.mark_non_differentiable(idx)
         return idx
 
@@ -195,9 +246,18 @@ def ball_query_pair(radius0, nsample0, radius1, nsample1, xyz, new_xyz):
     P = new_xyz.size(1)
     idx0 = torch.zeros(B, P, nsample0, dtype=torch.int32, device=xyz.device)
     idx1 = torch.zeros(B, P, nsample1, dtype=torch.int32, device=xyz.device)
-    rc = _lib.lib().g4d_ball_query2(B, N, P, float(radius0), nsample0, _lib.ptr(idx0), float(radius1), nsample1,
-                                    _lib.ptr(idx1), _lib.ptr(new_xyz), _lib.ptr(xyz), _lib.stream_ptr())
-    _lib.check(rc, "g4d_ball_query2")
+    if GRID_MIN_POINTS <= N <= 65536:
+        rmax = max(float(radius0), float(radius1))
+        grid = _cached_grid(xyz, rmax)
+        if grid is None:
+            grid = build_grid(xyz, rmax)
+        rc = _lib.lib().g4d_ball_query2_grid(B, N, P, float(radius0), nsample0, _lib.ptr(idx0), float(radius1), nsample1,
+                                             _lib.ptr(idx1), _lib.ptr(new_xyz), _lib.ptr(grid), _lib.stream_ptr())
+        _lib.check(rc, "g4d_ball_query2_grid")
+    else:
+        rc = _lib.lib().g4d_ball_query2(B, N, P, float(radius0), nsample0, _lib.ptr(idx0), float(radius1), nsample1,
+                                        _lib.ptr(idx1), _lib.ptr(new_xyz), _lib.ptr(xyz), _lib.stream_ptr())
+        _lib.check(rc, "g4d_ball_query2")
     return idx0, idx1
 
 

@@ -91,6 +91,18 @@ int g4d_ball_query2(int b, int n, int m, float radius0, int nsample0, int* idx0,
 int g4d_query_and_group(int b, int n, int m, int c, float radius, int nsample, int use_xyz, const float* xyz,
                         const float* new_xyz, const float* features, int* idx, float* out, void* stream);
 
+/* Uniform-grid acceleration of the neighbour searches; results identical to the brute-force entry points above.
+ * g4d_grid_build sorts each cloud's points by cell (cell edge >= min_cell, grown until <= 4096 cells; min_cell <= -1:
+ * automatic, -min_cell cells along the longest axis).  grid: device buffer of g4d_grid_bytes(b,n), 16-byte aligned. */
+size_t g4d_grid_bytes(int b, int n);
+int g4d_grid_build(int b, int n, const float* xyz, float min_cell, void* grid, void* stream);
+/* = g4d_ball_query2 (idx1 = NULL: = g4d_ball_query) given a grid over xyz with min_cell >= max radius; n <= 65536 */
+int g4d_ball_query2_grid(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
+                         const float* new_xyz, const void* grid, void* stream);
+/* = g4d_three_nn given a grid over the KNOWN points; unknown_grid (optional) only fixes a coherent processing order */
+int g4d_three_nn_grid(int b, int n, int m, const float* unknown, const void* known_grid, const void* unknown_grid,
+                      float* dist2, int* idx, void* stream);
+
 /* Grouped shared-MLP + max-pool on the tcgen05 tensor cores: for every centroid p, gathers its nsample
  * neighbours' [xyz - centroid, features] rows, runs the 3-layer 1x1-conv MLP (eval-mode BatchNorm folded
  * into weight/bias, ReLU) and max-pools over the neighbourhood -- SharedMLP + F.max_pool2d of
@@ -117,6 +129,24 @@ int g4d_sa_mlp_pack_params(const g4d_sa_mlp_desc* d, const float* w1, const floa
 int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int b, int n, int m, const float* xyz,
                    const float* new_xyz, const int* idx, const void* feat_pm, float* out_cm, void* out_pm,
                    int out_c_total, int out_c_off, void* stream);
+
+/* Fused feature propagation (no skip features) + optional segmentation head on tcgen05: inverse-distance weights
+ * from three_nn's squared distances, 3-tap interpolation, the FP module's 2-layer 1x1-conv MLP (eval BN folded, ReLU)
+ * and, when h1 > 0, Conv1d(c2,h1)+BN+ReLU -> Conv1d(h1,h2) -- PointnetFPModule.forward (pointnet2_modules.py:131-156)
+ * + FC_layer (modules/pointnet2encoder.py:98-101,143) for the finest level, in one kernel. */
+typedef struct g4d_fp_desc {
+    int c_in;          /* channels of the known (coarse) features = K of layer 1; multiple of 16, <= 256   */
+    int c1, c2;        /* FP MLP widths, multiples of 16, <= 256                                          */
+    int h1, h2;        /* head: hidden width (multiple of 16) and classes (<= 16); h1 = 0: no head        */
+} g4d_fp_desc;
+size_t g4d_fp_param_bytes(const g4d_fp_desc* d);
+/* host fp32 folded weights: w1 (c1,c_in), w2 (c2,c1), wh1 (h1,c2), wh2 (h2,h1) and biases -> blob (host memory) */
+int g4d_fp_pack_params(const g4d_fp_desc* d, const float* w1, const float* b1, const float* w2, const float* b2,
+                       const float* wh1, const float* bh1, const float* wh2, const float* bh2, void* blob);
+/* dist2/idx (b,n,3) as written by g4d_three_nn; known_pm: point-major fp16 (b,m,c_in);
+ * out_feat (b,c2,n) fp32 channel-major; out_head (b,n,h2) fp32 (NULL when h1 = 0). */
+int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int b, int n, int m, const float* dist2, const int* idx,
+                      const void* known_pm, float* out_feat, float* out_head, void* stream);
 
 /* ---- 3. SMPL linear-blend skinning (smplx/smplx/lbs.py) ----------------------------------------- */
 

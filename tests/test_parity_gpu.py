@@ -182,3 +182,59 @@ def test_full_size_properties(cuda):
     first = bq[:, :, :1]
     inc = (bq[:, :, 1:] > bq[:, :, :-1]) | (bq[:, :, 1:] == first)
     assert bool(inc.all())
+
+
+def _brute_ball(radius, K, x, new_xyz):
+    from garment4d_b200 import pointnet2_cuda
+    B, N, _ = x.shape
+    idx = torch.zeros(B, new_xyz.shape[1], K, dtype=torch.int32, device=x.device)
+    pointnet2_cuda.ball_query_wrapper(B, N, new_xyz.shape[1], radius, K, new_xyz, x, idx)
+    return idx
+
+
+def _brute_nn(u, k):
+    from garment4d_b200 import pointnet2_cuda
+    B, n, _ = u.shape
+    d2 = torch.empty(B, n, 3, device=u.device)
+    idx = torch.empty(B, n, 3, dtype=torch.int32, device=u.device)
+    pointnet2_cuda.three_nn_wrapper(B, n, k.shape[1], u, k, d2, idx)
+    return d2, idx
+
+
+@pytest.mark.parametrize("shape", ["body", "cube", "coincident", "outlier", "line", "planar_dups"])
+def test_grid_searches_equal_brute_force(cuda, shape):
+    """The uniform-grid ball query / three_nn must reproduce the brute-force kernels bit for bit on awkward clouds."""
+    B, N, m = 2, 4096, 600
+    rs = np.random.RandomState(77)
+    if shape in ("body", "cube"):
+        xyz = clouds(61, B, N, shape, dup_frac=0.1)
+    elif shape == "coincident":
+        xyz = np.full((B, N, 3), 0.25, np.float32)
+    elif shape == "outlier":
+        xyz = clouds(62, B, N, "body")
+        xyz[:, 7] = 1e6
+        xyz[:, 9] = -3e5
+    elif shape == "line":
+        xyz = np.zeros((B, N, 3), np.float32)
+        xyz[..., 0] = rs.rand(B, N).astype(np.float32)
+    else:
+        xyz = np.zeros((B, N, 3), np.float32)
+        xyz[..., :2] = (rs.randint(0, 40, (B, N, 2)) * 0.025).astype(np.float32)     # lattice: many exact distance ties
+    x = _t(xyz, cuda)
+    _, new_xyz = pu.furthest_point_sample_and_gather(x, m)
+    for radius, K in ((0.05, 16), (0.1, 32), (0.3, 64), (5.0, 128)):
+        got = pu.ball_query(radius, K, x, new_xyz)
+        assert torch.equal(got, _brute_ball(radius, K, x, new_xyz)), f"grid ball query differs (r={radius})"
+    a, b = pu.ball_query_pair(0.05, 16, 0.1, 32, x, new_xyz)
+    assert torch.equal(a, _brute_ball(0.05, 16, x, new_xyz)) and torch.equal(b, _brute_ball(0.1, 32, x, new_xyz))
+    # three_nn: unknown = whole cloud (grid order available from the ball query above), known = the 600 centroids
+    d, i = pu.three_nn(x, new_xyz)
+    d2b, ib = _brute_nn(x, new_xyz)
+    assert torch.equal(i, ib), "grid three_nn indices differ"
+    assert torch.equal(d, torch.sqrt(d2b))
+    # queries outside the cloud's bounding box
+    far = new_xyz + 0.07
+    assert torch.equal(pu.ball_query(0.1, 32, x, far), _brute_ball(0.1, 32, x, far))
+    d, i = pu.three_nn((x + 0.3).contiguous(), new_xyz)
+    d2b, ib = _brute_nn((x + 0.3).contiguous(), new_xyz)
+    assert torch.equal(i, ib) and torch.equal(d, torch.sqrt(d2b))
