@@ -16,30 +16,9 @@
 // Work drops from N*P (8192*1024 per cloud at SA1) distance tests to ~a few hundred per query.
 #include <float.h>
 #include "common.cuh"
+#include "grid.cuh"
 
 namespace g4d {
-
-constexpr int GRID_MAX_CELLS = 4096;
-constexpr int GRID_HDR = 16;                 // 4-byte words
-// per-cloud grid record: [hdr 16 words][cell_start GRID_MAX_CELLS+1 ints][pad to 16 B][sorted float4 n]
-struct GridHdr {
-    float ox, oy, oz, inv_h;
-    int dx, dy, dz, ncells;
-    float h;
-    int pad[7];
-};
-static_assert(sizeof(GridHdr) == GRID_HDR * 4, "GridHdr layout");
-
-__host__ __device__ inline size_t grid_cloud_words(int n) {
-    size_t w = GRID_HDR + (GRID_MAX_CELLS + 1);
-    w = (w + 3) / 4 * 4;
-    return w + (size_t)n * 4;
-}
-__device__ __forceinline__ const GridHdr* grid_hdr(const float* g) { return reinterpret_cast<const GridHdr*>(g); }
-__device__ __forceinline__ const int* grid_cell_start(const float* g) { return reinterpret_cast<const int*>(g) + GRID_HDR; }
-__device__ __forceinline__ const float4* grid_sorted(const float* g) {
-    return reinterpret_cast<const float4*>(g + (GRID_HDR + GRID_MAX_CELLS + 1 + 3) / 4 * 4);
-}
 
 __device__ __forceinline__ int cell_coord(float v, float o, float inv_h, int dim) {
     const int c = __float2int_rd(__fmul_rn(__fsub_rn(v, o), inv_h));     // NaN -> 0
@@ -157,6 +136,7 @@ ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_x
         for (int w = lane; w < nwords; w += 32) bm[s][w] = 0u;
     __syncwarp();
     const float r2[2] = {r2_0, r2_1};
+    const float r2max = NS > 1 ? fmaxf(r2_0, r2_1) : r2_0;
     const int KK[2] = {K0, K1};
     int* outs[2] = {idx0_all + cloud * (size_t)m * K0, NS > 1 ? idx1_all + cloud * (size_t)m * K1 : nullptr};
     const int wpl = (nwords + 31) / 32;      // bitmap words per lane (consecutive)
@@ -168,19 +148,32 @@ ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_x
         const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
         const int cx = cell_coord(qx, H.ox, H.inv_h, H.dx), cy = cell_coord(qy, H.oy, H.inv_h, H.dy), cz = cell_coord(qz, H.oz, H.inv_h, H.dz);
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, H.dx - 1);
-        for (int zz = max(cz - 1, 0); zz <= min(cz + 1, H.dz - 1); ++zz)
-            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, H.dy - 1); ++yy) {
+        // The 27 neighbour cells are 9 contiguous runs of the sorted array (x is the fastest cell index).  Lanes 0..8
+        // fetch one run's bounds each (one memory latency instead of nine), the runs are concatenated with a prefix
+        // sum, and all 32 lanes then walk the concatenation.
+        int beg = 0, len = 0;
+        if (lane < 9) {
+            const int zz = cz + lane / 3 - 1, yy = cy + lane % 3 - 1;
+            if (zz >= 0 && zz < H.dz && yy >= 0 && yy < H.dy) {
                 const int row = (zz * H.dy + yy) * H.dx;
-                const int beg = __ldg(cell_start + row + x0), end = __ldg(cell_start + row + x1 + 1);
-                for (int j = beg + lane; j < end; j += 32) {
-                    const float4 p = __ldg(sorted + j);
-                    const float d2 = sqdist_ref(qx - p.x, qy - p.y, qz - p.z);
+                beg = __ldg(cell_start + row + x0);
+                len = __ldg(cell_start + row + x1 + 1) - beg;
+            }
+        }
+        for (int r = 0; r < 9; ++r) {
+            const int rb = __shfl_sync(0xFFFFFFFFu, beg, r), re = rb + __shfl_sync(0xFFFFFFFFu, len, r);
+            for (int j = rb + lane; j < re; j += 32) {
+                const float4 p = __ldg(sorted + j);
+                const float d2 = sqdist_ref(qx - p.x, qy - p.y, qz - p.z);
+                if (d2 < r2max) {                                   // warp-divergent, but most candidates fail here
                     const unsigned k = (unsigned)__float_as_int(p.w);
+                    const unsigned bit = 1u << (k & 31);
 #pragma unroll
                     for (int s = 0; s < NS; ++s)
-                        if (d2 < r2[s]) atomicOr(&bm[s][k >> 5], 1u << (k & 31));
+                        if (d2 < r2[s]) atomicOr(&bm[s][k >> 5], bit);
                 }
             }
+        }
         __syncwarp();
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
@@ -268,8 +261,17 @@ three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const 
                 }
             }
         }
-        // every unvisited known point is at least R*h away along some axis; 0.998 keeps the test conservative under rounding
-        const float bound = (float)R * H.h;
+        // Every unvisited known point lies outside the visited block of cells along at least one axis, on a side where
+        // the grid continues; its distance is at least the gap from the query to that face.  0.998 keeps the stop
+        // test conservative under rounding of the cell assignment and of these face coordinates.
+        float bound = INFINITY;
+        if (cx - R > 0) bound = fminf(bound, ux - (H.ox + (float)(cx - R) * H.h));
+        if (cx + R < H.dx - 1) bound = fminf(bound, (H.ox + (float)(cx + R + 1) * H.h) - ux);
+        if (cy - R > 0) bound = fminf(bound, uy - (H.oy + (float)(cy - R) * H.h));
+        if (cy + R < H.dy - 1) bound = fminf(bound, (H.oy + (float)(cy + R + 1) * H.h) - uy);
+        if (cz - R > 0) bound = fminf(bound, uz - (H.oz + (float)(cz - R) * H.h));
+        if (cz + R < H.dz - 1) bound = fminf(bound, (H.oz + (float)(cz + R + 1) * H.h) - uz);
+        bound = fmaxf(bound, 0.f);
         if (b3 < bound * bound * 0.998f) break;
     }
     float* od = dist2_all + (cloud * n + pt) * 3;

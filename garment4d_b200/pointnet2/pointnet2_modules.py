@@ -107,6 +107,8 @@ class _PointnetSAModuleBase(nn.Module):
     def _forward_fused(self, xyz, features, new_xyz):
         B, N, _ = xyz.shape
         xyz = xyz.contiguous()
+        if N >= pointnet2_utils.GRID_MIN_POINTS and pointnet2_utils._cached_grid(xyz, max(g.radius for g in self.groupers)) is None:
+            pointnet2_utils.build_grid(xyz, max(g.radius for g in self.groupers))      # shared by FPS pruning and the ball query
         if new_xyz is None:
             _, new_xyz = pointnet2_utils.furthest_point_sample_and_gather(xyz, self.npoint)
         else:

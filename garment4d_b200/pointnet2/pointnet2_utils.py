@@ -35,6 +35,7 @@ def _f32(*shape, device):
 
 
 GRID_MIN_POINTS = 2048     # below this the brute-force scans are already cheap
+FPS_PRUNE_MIN_POINTS = 2048
 
 
 def build_grid(xyz: torch.Tensor, min_cell: float) -> torch.Tensor:
@@ -90,6 +91,15 @@ def furthest_point_sample_and_gather(xyz: torch.Tensor, npoint: int) -> Tuple[to
     B, N, _ = xyz.size()
     idx = _i32(B, npoint, device=xyz.device)
     new_xyz = _f32(B, npoint, 3, device=xyz.device)
+    if FPS_PRUNE_MIN_POINTS <= N <= 8192:
+        # exact spatial pruning over the cell-sorted order (any grid over xyz will do; an SA module builds it with its
+        # largest ball-query radius first, so the ball query that follows re-uses it)
+        grid = _cached_grid(xyz)
+        if grid is None:
+            grid = build_grid(xyz, -24.0)
+        rc = _lib.lib().g4d_fps_gather_grid(B, N, npoint, _lib.ptr(grid), _lib.ptr(idx), _lib.ptr(new_xyz), _lib.stream_ptr())
+        _lib.check(rc, "g4d_fps_gather_grid")
+        return idx, new_xyz
     scratch = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device) if N > 16384 else None
     rc = _lib.lib().g4d_fps_gather(B, N, npoint, _lib.ptr(xyz), _lib.ptr(idx), _lib.ptr(new_xyz), _lib.ptr(scratch),
                                    _lib.stream_ptr())
@@ -150,7 +160,7 @@ def three_nn_raw(unknown, known, dist2, idx):
     B, N, _ = unknown.size()
     m = known.size(1)
     if N >= GRID_MIN_POINTS and 512 <= m <= (1 << 20):
-        kgrid = build_grid(known, -max(4.0, round(float(m) ** 0.5 / 2)))
+        kgrid = build_grid(known, -max(4.0, round(0.7 * float(m) ** 0.5)))
         ugrid = _cached_grid(unknown)      # only a processing order: any grid over `unknown` will do
         rc = _lib.lib().g4d_three_nn_grid(B, N, m, _lib.ptr(unknown), _lib.ptr(kgrid), _lib.ptr(ugrid), _lib.ptr(dist2),
                                           _lib.ptr(idx), _lib.stream_ptr())

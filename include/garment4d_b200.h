@@ -96,6 +96,9 @@ int g4d_query_and_group(int b, int n, int m, int c, float radius, int nsample, i
  * automatic, -min_cell cells along the longest axis).  grid: device buffer of g4d_grid_bytes(b,n), 16-byte aligned. */
 size_t g4d_grid_bytes(int b, int n);
 int g4d_grid_build(int b, int n, const float* xyz, float min_cell, void* grid, void* stream);
+/* = g4d_fps_gather (identical idx / new_xyz) given any grid over xyz: threads own compact clumps of the cell-sorted
+ * points and skip, exactly, every min-distance update that cannot change anything.  1 <= n <= 8192. */
+int g4d_fps_gather_grid(int b, int n, int m, const void* grid, int* idx, float* new_xyz, void* stream);
 /* = g4d_ball_query2 (idx1 = NULL: = g4d_ball_query) given a grid over xyz with min_cell >= max radius; n <= 65536 */
 int g4d_ball_query2_grid(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
                          const float* new_xyz, const void* grid, void* stream);
