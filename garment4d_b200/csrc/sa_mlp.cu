@@ -4,27 +4,29 @@
 //     grouping_operation(xyz) - centroid ; grouping_operation(features) ; cat        (pointnet2_utils.py:250-258)
 //     3 x [cuDNN 1x1 Conv2d -> BatchNorm2d -> ReLU]                                  (pytorch_utils.py:5-32)
 //     F.max_pool2d(kernel=[1, nsample]) ; squeeze ; (torch.cat over scales)          (pointnet2_modules.py:42-55)
-// i.e. 9+ kernels that each stream the (B, C, npoint, nsample) activation through HBM, with ONE persistent
-// kernel that never materialises the grouped tensor:
+// i.e. 9+ kernels that each stream the (B, C, npoint, nsample) activation through HBM, with ONE persistent,
+// warp-specialised kernel that never materialises the grouped tensor:
 //
-//   per 128-row tile (= 128/nsample whole neighbourhoods):
-//     gather  : rows [features(idx) | xyz(idx) - centroid] are written straight into the UMMA canonical
-//               K-major shared-memory layout (fp16; the 3 relative coordinates are split hi+lo so that the
-//               geometry enters the first layer at ~fp32 precision)
-//     layer 1 : D1[128 x c1]  = A0[128 x k0] . W1^T      tcgen05.mma kind::f16, fp32 accumulate in TMEM
-//     epi 1   : TMEM -> regs (+bias, ReLU, ->fp16) -> shared (canonical layout again)
-//     layer 2 : D2[128 x c2]  = H1 . W2^T
-//     epi 2   : as epi 1
-//     layer 3 : D3[c3 x 128]  = W3 . H2^T   -- TRANSPOSED: channels on TMEM lanes, positions on columns, so the
-//               max over a neighbourhood is a max over nsample consecutive columns inside ONE thread
-//     epi 3   : max over each neighbourhood, + bias, ReLU (max and the monotone bias+ReLU commute), written
-//               channel-major fp32 at the scale's channel offset (fuses torch.cat) and, optionally,
-//               point-major fp16 for the next level's gather.
+//   producer warps (8)  one thread per row of the 128-row tile (= 128/nsample whole neighbourhoods): idx -> point id,
+//                       relative xyz (fp32 subtract, then hi/lo fp16 split so the geometry enters layer 1 at ~fp32
+//                       precision), and the neighbour's fp16 feature row streamed 32 B at a time into a ring of
+//                       16-channel K-slices in shared memory, already in the UMMA canonical K-major layout.
+//                       full/empty mbarriers per ring slot; the producers run up to a whole tile ahead.
+//   MMA warp (1 lane)   layer 1: D1[128 x c1] += slice . W1_slice^T, one tcgen05.mma (kind::f16, fp32 accumulate in
+//                       TMEM) per slice as it lands; tcgen05.commit frees the slot.
+//                       layer 2: D2[128 x c2] = H1 . W2^T ;  layer 3 TRANSPOSED: D3[c3 x 128] = W3 . H2^T, so that
+//                       channels sit on TMEM lanes, positions on columns, and the max over a neighbourhood is a max
+//                       over nsample consecutive columns inside ONE thread.
+//   epilogue warps (8)  tcgen05.ld -> +bias, ReLU, fp16 (cvt.rn.relu.satfinite) -> shared (canonical layout) for
+//                       layers 1-2; layer 3: neighbourhood max, +bias, ReLU (max and the monotone bias+ReLU commute),
+//                       written channel-major fp32 at the scale's channel offset (fuses torch.cat) and, optionally,
+//                       point-major fp16 for the next level's gather.
 //   Folded weights of all three layers stay resident in shared memory (one cp.async.bulk / TMA bulk copy per CTA).
 //
 // Shared-memory operand layout ("canonical K-major, no swizzle", cute::UMMA::LayoutType::SWIZZLE_NONE):
 //   element (row r, k) of an operand with R rows lives at byte ((k/8)*R + r)*16 + (k%8)*2
 //   => core matrix = 8 rows x 16 B contiguous; SBO (next 8-row group) = 128 B; LBO (next K chunk) = R*16 B.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -33,13 +35,17 @@
 namespace g4d {
 
 constexpr int TILE_M = 128;
-constexpr int SA_THREADS = 128;
-constexpr int XYZ_SLOTS = 9;     // [hi(3) | lo(3) | hi(3)] against weights [wh | wh | wl]
+constexpr int XYZ_SLOTS = 9;                 // [hi(3) | lo(3) | hi(3)] against weights [wh | wh | wl]
+constexpr int SA_EPI_WARPS = 8, SA_PROD_WARPS = 8;   // 2 epilogue warps per TMEM lane quadrant (they split the columns)
+constexpr int SA_THREADS = (SA_EPI_WARPS + 1 + SA_PROD_WARPS) * 32;     // 544
+constexpr int SLICE_BYTES = TILE_M * 16 * 2;  // one K-slice: 128 rows x 16 channels fp16 = 4 KB
+constexpr int MAX_RING = 16;
 
 struct SaMlpLayout {
-    int k0, c1, c2, c3, c3p, nb3;
+    int k0, c1, c2, c3, c3p, nb3, nslices, ring, tb;        // tb = tiles per batch (hand-off latency amortised over tb tiles)
+    uint32_t h_bytes, cstride;                              // per-tile H buffer bytes, per-tile TMEM column stride
     uint32_t off_w1, off_w2, off_w3, off_b1, off_b2, off_b3, blob_bytes;   // inside the parameter blob == smem image
-    uint32_t off_act, act_bytes, off_rowpt, off_bar, total_smem;
+    uint32_t off_h, off_ring, off_bar, total_smem;
     uint32_t tmem_cols;
 };
 
@@ -58,6 +64,7 @@ static bool make_layout(const g4d_sa_mlp_desc* d, SaMlpLayout* L, const char** w
     L->k0 = d->k0; L->c1 = d->c1; L->c2 = d->c2; L->c3 = d->c3;
     L->c3p = d->c3 <= 128 ? 128 : 256;
     L->nb3 = L->c3p / 128;
+    L->nslices = L->k0 / 16;
     uint32_t o = 0;
     L->off_w1 = o; o += (uint32_t)L->k0 * L->c1 * 2;
     L->off_w2 = o; o += (uint32_t)L->c1 * L->c2 * 2;
@@ -66,20 +73,57 @@ static bool make_layout(const g4d_sa_mlp_desc* d, SaMlpLayout* L, const char** w
     L->off_b2 = o; o += (uint32_t)L->c2 * 4;
     L->off_b3 = o; o += (uint32_t)L->c3p * 4;
     L->blob_bytes = o;                                   // multiple of 16 by construction
-    int kmax = L->k0 > L->c1 ? L->k0 : L->c1;
-    if (L->c2 > kmax) kmax = L->c2;
-    L->off_act = round_up(o, 128);
-    L->act_bytes = (uint32_t)TILE_M * kmax * 2;
-    L->off_rowpt = L->off_act + L->act_bytes;
-    L->off_bar = L->off_rowpt + TILE_M * 4;
-    L->total_smem = L->off_bar + 64;
-    uint32_t cols = L->c1 > L->c2 ? L->c1 : L->c2;
-    if ((uint32_t)(128 * L->nb3) > cols) cols = 128 * L->nb3;
+    const int hk = L->c1 > L->c2 ? L->c1 : L->c2;
+    L->h_bytes = (uint32_t)TILE_M * hk * 2;
+    L->cstride = (uint32_t)(128 * L->nb3) > (uint32_t)hk ? 128 * L->nb3 : hk;
+    L->off_h = round_up(o, 128);
+    const uint32_t budget = 227u * 1024u - 512u;
+    // tiles per batch: as many as TMEM (512 columns) and shared memory allow, up to 4 (env G4D_SA_TB overrides)
+    int tb = 512 / (int)L->cstride;
+    if (tb > 4) tb = 4;
+    if (tb == 3) tb = 2;
+    if (const char* e = getenv("G4D_SA_TB")) { const int v = atoi(e); if (v >= 1 && v <= tb) tb = v; }
+    while (tb > 1 && L->off_h + (uint32_t)tb * L->h_bytes + 4u * SLICE_BYTES > budget) tb >>= 1;
+    L->tb = tb;
+    L->off_ring = L->off_h + (uint32_t)tb * L->h_bytes;
+    // ring depth: two tiles' worth of slices when they fit (producers run ahead), at least 2, at most 16
+    int ring = 2 * L->nslices;
+    if (ring < 4) ring = 4;
+    if (ring > MAX_RING) ring = MAX_RING;
+    while (ring > 2 && L->off_ring + (uint32_t)ring * SLICE_BYTES > budget) --ring;
+    L->ring = ring;
+    L->off_bar = L->off_ring + (uint32_t)ring * SLICE_BYTES;
+    L->total_smem = L->off_bar + 8 * (2 * MAX_RING + 4) + 16;
     uint32_t p2 = 32;
-    while (p2 < cols) p2 <<= 1;
+    while (p2 < (uint32_t)tb * L->cstride) p2 <<= 1;
     L->tmem_cols = p2;
     if (L->total_smem > 227 * 1024) { *why = msgs[5]; return false; }
     return true;
+}
+
+// NB x 16 consecutive TMEM columns of this thread's lane: all loads in flight, ONE wait
+template <int NB>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+    uint32_t r[NB * 16];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+            : "=r"(r[16 * b + 0]), "=r"(r[16 * b + 1]), "=r"(r[16 * b + 2]), "=r"(r[16 * b + 3]), "=r"(r[16 * b + 4]),
+              "=r"(r[16 * b + 5]), "=r"(r[16 * b + 6]), "=r"(r[16 * b + 7]), "=r"(r[16 * b + 8]), "=r"(r[16 * b + 9]),
+              "=r"(r[16 * b + 10]), "=r"(r[16 * b + 11]), "=r"(r[16 * b + 12]), "=r"(r[16 * b + 13]), "=r"(r[16 * b + 14]),
+              "=r"(r[16 * b + 15])
+            : "r"(taddr + 16 * b));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < NB * 16; ++i) {
+        asm volatile("" : "+r"(r[i]));            // pin: no use of r[i] may be scheduled above the wait
+        v[i] = __uint_as_float(r[i]);
+    }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -87,7 +131,8 @@ static bool make_layout(const g4d_sa_mlp_desc* d, SaMlpLayout* L, const char** w
 struct SaMlpArgs {
     SaMlpLayout L;
     int c_in, nsample, n, m;
-    long long total_rows;            // b * m * nsample
+    int total_rows;                  // b * m * nsample (< 2^31, checked on the host)
+    int lg_ns, lg_tb;                // log2(nsample), log2(tiles per batch): divisions become shifts
     int ntiles;
     const float* xyz;                // (b, n, 3)
     const float* new_xyz;            // (b, m, 3)
@@ -104,195 +149,374 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const SaMlpLayout& L = a.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char* act = smem + L.off_act;
-    uint32_t* rowpt = reinterpret_cast<uint32_t*>(smem + L.off_rowpt);
+    unsigned char* hbuf = smem + L.off_h;
     const float* b1 = reinterpret_cast<const float*>(smem + L.off_b1);
     const float* b2 = reinterpret_cast<const float*>(smem + L.off_b2);
     const float* b3 = reinterpret_cast<const float*>(smem + L.off_b3);
-    const uint32_t bar_w = smem_u32(smem + L.off_bar), bar_mma = bar_w + 8, tmem_slot = bar_w + 16;
+    // barriers: [0] weights, [1] d_full (MMA -> epilogue), [2] epi_done (epilogue -> MMA), [3] tmem slot,
+    //           [4 .. 4+MAX_RING) full[r], [4+MAX_RING .. 4+2*MAX_RING) empty[r]
+    const uint32_t bar0 = smem_u32(smem + L.off_bar);
+    const uint32_t bar_w = bar0, bar_dfull = bar0 + 8, bar_epi = bar0 + 16, tmem_slot = bar0 + 24;
+    const uint32_t bar_full = bar0 + 32, bar_empty = bar0 + 32 + 8 * MAX_RING;
     const uint32_t s_w1 = smem_u32(smem + L.off_w1), s_w2 = smem_u32(smem + L.off_w2), s_w3 = smem_u32(smem + L.off_w3);
-    const uint32_t s_act = smem_u32(act);
+    const uint32_t s_h = smem_u32(hbuf), s_ring = smem_u32(smem + L.off_ring);
 
     if (tid == 0) {
         mbar_init(bar_w, 1);
-        mbar_init(bar_mma, 1);
+        mbar_init(bar_dfull, 1);
+        mbar_init(bar_epi, SA_EPI_WARPS);
+        for (int r = 0; r < L.ring; ++r) { mbar_init(bar_full + 8 * r, 4);     /* the 4 warps of the producer group that owns the slot's tile */ mbar_init(bar_empty + 8 * r, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(tmem_slot, L.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L.off_bar + 16);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L.off_bar + 24);
     if (tid == 0) {
         mbar_expect_tx(bar_w, L.blob_bytes);
         bulk_g2s(smem_u32(smem), a.params, L.blob_bytes, bar_w);      // folded weights + biases, once per CTA
     }
-    mbar_wait(bar_w, 0);
 
-    const int nchunk_feat = a.c_in >> 3;            // 16-byte chunks of feature channels per row
-    const int nchunk_k0 = L.k0 >> 3;
-    const int groups_per_tile = TILE_M / a.nsample;
-    const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    uint32_t phase = 0;
+    const int S = L.nslices, RING = L.ring;
 
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        // ---------------- gather: build A0[128 x k0] in canonical layout -------------------------------
-        {
-            const long long R = (long long)tile * TILE_M + tid;       // global row = (cloud, centroid, sample)
-            uint32_t pt = 0xFFFFFFFFu;
-            uint4 c0 = make_uint4(0, 0, 0, 0), c1v = make_uint4(0, 0, 0, 0);
-            if (R < a.total_rows) {
-                const long long gp = R / a.nsample;                   // global centroid
-                const int cloud = (int)(gp / a.m);
-                const int src = __ldg(a.idx + R);
-                pt = (uint32_t)((long long)cloud * a.n + src);
-                const float* p = a.xyz + (size_t)pt * 3;
+    if (warp >= SA_EPI_WARPS + 1) {
+        // =========================== PRODUCERS: one thread per tile row ===================================
+        // Two groups of 4 warps take alternate tiles of this CTA's tile sequence (ring slots are addressed by the
+        // global slice counter seq * S + s, so both groups fill the ring concurrently and in order).  Inside a group
+        // the loads are software-pipelined: idx two tiles ahead, coordinates one tile ahead, feature chunks one batch
+        // (8 x 16 B per thread) ahead of the stores.  All index arithmetic is 32-bit (sizes checked on the host) and
+        // nsample / tiles-per-batch are powers of two; the code is written flat on purpose (no helper objects: the
+        // per-tile instruction count of this role bounds the small layers).
+        const int pw = warp - (SA_EPI_WARPS + 1);
+        const int grp = pw >> 2;
+        const int r = (pw & 3) * 32 + lane;                      // tile row 0..127
+        const int nchunk_feat = a.c_in >> 3;
+        const int lg_tb = a.lg_tb, tbm = L.tb - 1, lg_ns = a.lg_ns;
+        const int bx = (int)blockIdx.x, gx = (int)gridDim.x;
+        const unsigned um = (unsigned)a.m;
+#define G4D_TILE_OF(q) ((((bx + ((q) >> lg_tb) * gx)) << lg_tb) + ((q) & tbm))
+        int seq = grp;
+        int t_cur = G4D_TILE_OF(seq), t_nxt = G4D_TILE_OF(seq + 2);
+        // pipeline registers: source index of the next two tiles, geometry + point id of the next tile
+        int src_n = 0, src_nn = 0;
+        float npx = 0.f, npy = 0.f, npz = 0.f, nqx = 0.f, nqy = 0.f, nqz = 0.f;
+        unsigned npt = 0;
+        if (t_cur < a.ntiles && t_cur * TILE_M + r < a.total_rows) src_n = __ldg(a.idx + t_cur * TILE_M + r);
+        if (t_nxt < a.ntiles && t_nxt * TILE_M + r < a.total_rows) src_nn = __ldg(a.idx + t_nxt * TILE_M + r);
+        if (t_cur < a.ntiles && t_cur * TILE_M + r < a.total_rows) {
+            const unsigned gp = (unsigned)(t_cur * TILE_M + r) >> lg_ns;
+            npt = (gp / um) * (unsigned)a.n + (unsigned)src_n;
+            const float* p = a.xyz + (size_t)npt * 3;
+            const float* q = a.new_xyz + (size_t)gp * 3;
+            npx = __ldg(p); npy = __ldg(p + 1); npz = __ldg(p + 2);
+            nqx = __ldg(q); nqy = __ldg(q + 1); nqz = __ldg(q + 2);
+        }
+        while (t_cur < a.ntiles) {
+            const int tile = t_cur;
+            const bool live = tile * TILE_M + r < a.total_rows;
+            const float dx = npx - nqx, dy = npy - nqy, dz = npz - nqz;
+            const unsigned pt = npt;
+            const uint32_t it0 = (uint32_t)seq * (uint32_t)S;      // global slice counter of this tile's first slice
+            // ---- advance the pipeline: issue the loads of the following tiles before touching this one
+            seq += 2;
+            t_cur = t_nxt;
+            t_nxt = G4D_TILE_OF(seq + 2);
+            src_n = src_nn;
+            src_nn = 0;
+            if (t_nxt < a.ntiles && t_nxt * TILE_M + r < a.total_rows) src_nn = __ldg(a.idx + t_nxt * TILE_M + r);
+            if (t_cur < a.ntiles && t_cur * TILE_M + r < a.total_rows) {
+                const unsigned gp = (unsigned)(t_cur * TILE_M + r) >> lg_ns;
+                npt = (gp / um) * (unsigned)a.n + (unsigned)src_n;
+                const float* p = a.xyz + (size_t)npt * 3;
                 const float* q = a.new_xyz + (size_t)gp * 3;
-                const float dx = __ldg(p) - __ldg(q), dy = __ldg(p + 1) - __ldg(q + 1), dz = __ldg(p + 2) - __ldg(q + 2);
+                npx = __ldg(p); npy = __ldg(p + 1); npz = __ldg(p + 2);
+                nqx = __ldg(q); nqy = __ldg(q + 1); nqz = __ldg(q + 2);
+            }
+            // ---- this tile: relative xyz, hi/lo split.  slots: hi.x hi.y hi.z lo.x lo.y lo.z hi.x hi.y | hi.z 0 ... 0
+            uint4 xc0 = make_uint4(0, 0, 0, 0), xc1 = make_uint4(0, 0, 0, 0);
+            if (live) {
                 const __half hx = __float2half_rn(dx), hy = __float2half_rn(dy), hz = __float2half_rn(dz);
-                const float lx = dx - __half2float(hx), ly = dy - __half2float(hy), lz = dz - __half2float(hz);
                 const uint32_t uhx = __half_as_ushort(hx), uhy = __half_as_ushort(hy), uhz = __half_as_ushort(hz);
-                const uint32_t ulx = __half_as_ushort(__float2half_rn(lx)), uly = __half_as_ushort(__float2half_rn(ly)),
-                               ulz = __half_as_ushort(__float2half_rn(lz));
-                // slots: hi.x hi.y hi.z lo.x lo.y lo.z hi.x hi.y | hi.z 0 0 0 0 0 0 0
-                c0 = make_uint4(uhx | (uhy << 16), uhz | (ulx << 16), uly | (ulz << 16), uhx | (uhy << 16));
-                c1v = make_uint4(uhz, 0, 0, 0);
+                const uint32_t ulx = __half_as_ushort(__float2half_rn(dx - __half2float(hx))),
+                               uly = __half_as_ushort(__float2half_rn(dy - __half2float(hy))),
+                               ulz = __half_as_ushort(__float2half_rn(dz - __half2float(hz)));
+                xc0 = make_uint4(uhx | (uhy << 16), uhz | (ulx << 16), uly | (ulz << 16), uhx | (uhy << 16));
+                xc1 = make_uint4(uhz, 0, 0, 0);
             }
-            rowpt[tid] = pt;
-            uint4* dst = reinterpret_cast<uint4*>(act);
-            dst[(size_t)nchunk_feat * TILE_M + tid] = c0;
-            dst[(size_t)(nchunk_feat + 1) * TILE_M + tid] = c1v;
-            for (int c = nchunk_feat + 2; c < nchunk_k0; ++c) dst[(size_t)c * TILE_M + tid] = make_uint4(0, 0, 0, 0);
-            __syncwarp();
-            if (nchunk_feat) {
-                // warp w owns rows 32w..32w+31: 8 rows x 4 chunks per step, 16 B per lane
-                const int rl = lane & 7, cl = lane >> 3;
-                for (int rg = 0; rg < 4; ++rg) {
-                    const int row = warp * 32 + rg * 8 + rl;
-                    const uint32_t rp = rowpt[row];
-                    const uint4* srcrow = reinterpret_cast<const uint4*>(a.feat_pm + (size_t)rp * a.c_in);
-                    for (int c = cl; c < nchunk_feat; c += 4) {
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (rp != 0xFFFFFFFFu) v = __ldg(srcrow + c);
-                        dst[(size_t)c * TILE_M + row] = v;
+            uint32_t it = it0;
+            if (nchunk_feat == 0) {
+                // xyz-only level: a single slice per tile
+                const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+                uint4* dst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
+                dst[r] = xc0;
+                dst[TILE_M + r] = xc1;
+                fence_proxy_async();                              // generic-proxy stores -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * slot);
+            } else {
+                const uint4* srcrow = reinterpret_cast<const uint4*>(a.feat_pm + (size_t)pt * a.c_in);
+                uint4 vc[8], vn[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    vc[e] = make_uint4(0, 0, 0, 0);
+                    if (e < nchunk_feat) { if (live) vc[e] = __ldg(srcrow + e); }
+                    else if (e == nchunk_feat) vc[e] = xc0;
+                    else if (e == nchunk_feat + 1) vc[e] = xc1;
+                }
+                for (int s0 = 0; s0 < S; s0 += 4) {
+                    if (s0 + 4 < S) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = ((s0 + 4) << 1) + e;    // 16-byte chunk index along K
+                            vn[e] = make_uint4(0, 0, 0, 0);
+                            if (c < nchunk_feat) { if (live) vn[e] = __ldg(srcrow + c); }
+                            else if (c == nchunk_feat) vn[e] = xc0;
+                            else if (c == nchunk_feat + 1) vn[e] = xc1;
+                        }
                     }
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        if (s0 + e2 < S) {                        // uniform
+                            const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                            mbar_wait(bar_empty + 8 * slot, ph ^ 1);      // slot free (first lap passes at once)
+                            uint4* dst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
+                            dst[r] = vc[2 * e2];
+                            dst[TILE_M + r] = vc[2 * e2 + 1];
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_full + 8 * slot);
+                            ++it;
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) vc[e] = vn[e];
                 }
             }
         }
-        fence_proxy_async();
-        __syncthreads();
-
-        // ---------------- layer 1 ----------------------------------------------------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t idesc = umma_idesc(TILE_M, L.c1);
-            for (int k = 0; k < L.k0 / 16; ++k) {
-                const uint64_t ad = umma_desc(s_act + (uint32_t)k * 2 * TILE_M * 16, TILE_M * 16, 128);
-                const uint64_t bd = umma_desc(s_w1 + (uint32_t)k * 2 * L.c1 * 16, L.c1 * 16, 128);
-                umma_f16(tmem, ad, bd, idesc, k > 0);
+#undef G4D_TILE_OF
+    } else if (warp == SA_EPI_WARPS) {
+        // =========================== MMA ISSUER (one lane) ==================================================
+        if (lane == 0) {
+            mbar_wait(bar_w, 0);
+            uint32_t it = 0, nepi = 0;                           // slices consumed; epilogue hand-offs waited for
+            const uint32_t idesc1 = umma_idesc(TILE_M, L.c1), idesc2 = umma_idesc(TILE_M, L.c2), idesc3 = umma_idesc(128, TILE_M);
+            for (long long tl = (long long)blockIdx.x * L.tb; tl < a.ntiles; tl += (long long)gridDim.x * L.tb) {
+                const int nb = (int)((a.ntiles - tl) < L.tb ? (a.ntiles - tl) : L.tb);      // tiles in this batch
+                // ---- layer 1: needs TMEM drained by the previous batch's epilogue 3
+                mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
+                tc_fence_after();
+                for (int bi = 0; bi < nb; ++bi)
+                    for (int s = 0; s < S; ++s) {
+                        const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                        mbar_wait(bar_full + 8 * slot, ph);
+                        tc_fence_after();
+                        const uint64_t ad = umma_desc(s_ring + slot * SLICE_BYTES, TILE_M * 16, 128);
+                        const uint64_t bd = umma_desc(s_w1 + (uint32_t)s * 2 * L.c1 * 16, L.c1 * 16, 128);
+                        umma_f16(tmem + bi * L.cstride, ad, bd, idesc1, s > 0);
+                        umma_commit(bar_empty + 8 * slot);        // slot reusable once this (and earlier) MMAs retire
+                        ++it;
+                    }
+                umma_commit(bar_dfull);
+                // ---- layer 2: needs H1 written by epilogue 1
+                mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
+                tc_fence_after();
+                for (int bi = 0; bi < nb; ++bi)
+                    for (int k = 0; k < L.c1 / 16; ++k) {
+                        const uint64_t ad = umma_desc(s_h + bi * L.h_bytes + (uint32_t)k * 2 * TILE_M * 16, TILE_M * 16, 128);
+                        const uint64_t bd = umma_desc(s_w2 + (uint32_t)k * 2 * L.c2 * 16, L.c2 * 16, 128);
+                        umma_f16(tmem + bi * L.cstride, ad, bd, idesc2, k > 0);
+                    }
+                umma_commit(bar_dfull);
+                // ---- layer 3, transposed: D3[c3p x 128] = W3 . H2^T
+                mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
+                tc_fence_after();
+                for (int bi = 0; bi < nb; ++bi)
+                    for (int j = 0; j < L.nb3; ++j)
+                        for (int k = 0; k < L.c2 / 16; ++k) {
+                            const uint64_t ad = umma_desc(s_w3 + (uint32_t)k * 2 * L.c3p * 16 + (uint32_t)j * 128 * 16, L.c3p * 16, 128);
+                            const uint64_t bd = umma_desc(s_h + bi * L.h_bytes + (uint32_t)k * 2 * TILE_M * 16, TILE_M * 16, 128);
+                            umma_f16(tmem + bi * L.cstride + j * 128, ad, bd, idesc3, k > 0);
+                        }
+                umma_commit(bar_dfull);
             }
-            umma_commit(bar_mma);
         }
-        mbar_wait(bar_mma, phase); phase ^= 1;
-        tc_fence_after();
-        // epilogue 1: row tid, bias + ReLU -> fp16 -> act (A0 is dead: MMA 1 has completed)
-        for (int c0 = 0; c0 < L.c1; c0 += 16) {
-            float v[16];
-            tmem_ld16(lane_taddr + c0, v);
-            uint32_t h[8];
+        __syncwarp();                                            // reconverge before the block-wide barrier below
+    } else {
+        // =========================== EPILOGUE: warps q and q+4 own TMEM lanes 32q .. 32q+31 ==================
+        mbar_wait(bar_w, 0);                                      // biases live in the weight blob
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;                         // tile row (layers 1-2) / channel within block (layer 3)
+        const uint32_t lane_taddr = tmem + ((uint32_t)(quad * 32) << 16);
+        const int groups_per_tile = TILE_M / a.nsample;
+        uint32_t nd = 0;                                          // d_full hand-offs waited for
+        // Work split between the two warps of a quadrant: with tb >= 2 tiles per batch each takes alternate tiles (all
+        // columns); with a single tile per batch they split its columns.
+        const bool split_cols = L.tb == 1;
+        auto relu_to_h = [&](int bi, int ncols, const float* bias) {
+            const int units = ncols / 16;
+            const int u0 = (!split_cols || half == 0) ? 0 : (units + 1) / 2;
+            const int u1 = (!split_cols) ? units : (half == 0 ? (units + 1) / 2 : units);
+            const uint32_t ta = lane_taddr + bi * L.cstride;
+            uint4* hd = reinterpret_cast<uint4*>(hbuf + (size_t)bi * L.h_bytes);
+            int u = u0;
+            for (; u + 2 <= u1; u += 2) {
+                float v[32];
+                tmem_ld_cols<2>(ta + 16 * u, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) h[i] = pack_relu_f16x2(v[2 * i] + b1[c0 + 2 * i], v[2 * i + 1] + b1[c0 + 2 * i + 1]);
-            uint4* dst = reinterpret_cast<uint4*>(act);
-            dst[(size_t)(c0 / 8) * TILE_M + tid] = make_uint4(h[0], h[1], h[2], h[3]);
-            dst[(size_t)(c0 / 8 + 1) * TILE_M + tid] = make_uint4(h[4], h[5], h[6], h[7]);
-        }
-        tc_fence_before();
-        fence_proxy_async();
-        __syncthreads();
-
-        // ---------------- layer 2 ----------------------------------------------------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t idesc = umma_idesc(TILE_M, L.c2);
-            for (int k = 0; k < L.c1 / 16; ++k) {
-                const uint64_t ad = umma_desc(s_act + (uint32_t)k * 2 * TILE_M * 16, TILE_M * 16, 128);
-                const uint64_t bd = umma_desc(s_w2 + (uint32_t)k * 2 * L.c2 * 16, L.c2 * 16, 128);
-                umma_f16(tmem, ad, bd, idesc, k > 0);
-            }
-            umma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, phase); phase ^= 1;
-        tc_fence_after();
-        for (int c0 = 0; c0 < L.c2; c0 += 16) {
-            float v[16];
-            tmem_ld16(lane_taddr + c0, v);
-            uint32_t h[8];
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t h[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) h[i] = pack_relu_f16x2(v[2 * i] + b2[c0 + 2 * i], v[2 * i + 1] + b2[c0 + 2 * i + 1]);
-            uint4* dst = reinterpret_cast<uint4*>(act);
-            dst[(size_t)(c0 / 8) * TILE_M + tid] = make_uint4(h[0], h[1], h[2], h[3]);
-            dst[(size_t)(c0 / 8 + 1) * TILE_M + tid] = make_uint4(h[4], h[5], h[6], h[7]);
-        }
-        tc_fence_before();
-        fence_proxy_async();
-        __syncthreads();
-
-        // ---------------- layer 3, transposed: D3[c3p x 128] = W3 . H2^T --------------------------------
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t idesc = umma_idesc(128, TILE_M);
-            for (int j = 0; j < L.nb3; ++j)
-                for (int k = 0; k < L.c2 / 16; ++k) {
-                    const uint64_t ad = umma_desc(s_w3 + (uint32_t)k * 2 * L.c3p * 16 + (uint32_t)j * 128 * 16, L.c3p * 16, 128);
-                    const uint64_t bd = umma_desc(s_act + (uint32_t)k * 2 * TILE_M * 16, TILE_M * 16, 128);
-                    umma_f16(tmem + j * 128, ad, bd, idesc, k > 0);
+                    for (int i = 0; i < 4; ++i)
+                        h[i] = pack_relu_f16x2(v[8 * q + 2 * i] + bias[16 * u + 8 * q + 2 * i], v[8 * q + 2 * i + 1] + bias[16 * u + 8 * q + 2 * i + 1]);
+                    hd[(size_t)(2 * u + q) * TILE_M + row] = make_uint4(h[0], h[1], h[2], h[3]);
                 }
-            umma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, phase); phase ^= 1;
-        tc_fence_after();
-        // epilogue 3: lane = output channel; max over each neighbourhood's nsample consecutive columns
-        for (int j = 0; j < L.nb3; ++j) {
-            const int ch = j * 128 + tid;
-            const float bias = b3[ch];
-            float run = -INFINITY;
-            for (int c0 = 0; c0 < TILE_M; c0 += 16) {
+            }
+            for (; u < u1; ++u) {
                 float v[16];
-                tmem_ld16(lane_taddr + j * 128 + c0, v);
-                if (a.nsample == 8) {
+                tmem_ld_cols<1>(ta + 16 * u, v);
 #pragma unroll
-                    for (int hgrp = 0; hgrp < 2; ++hgrp) {
-                        float mx = v[hgrp * 8];
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t h[4];
 #pragma unroll
-                        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[hgrp * 8 + i]);
-                        const long long gp = (long long)tile * groups_per_tile + (c0 >> 3) + hgrp;
-                        if (ch < L.c3 && gp * a.nsample < a.total_rows) {
-                            const float o = fmaxf(mx + bias, 0.f);
-                            const long long cloud = gp / a.m, p = gp - cloud * a.m;
-                            a.out_cm[((size_t)cloud * a.ctot + a.coff + ch) * a.m + p] = o;
-                            if (a.out_pm) a.out_pm[(size_t)gp * a.ctot + a.coff + ch] = __float2half_rn(fminf(o, 65504.f));
-                        }
-                    }
-                } else {
-                    float mx = v[0];
-#pragma unroll
-                    for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[i]);
-                    run = fmaxf(run, mx);
-                    if (((c0 + 16) % a.nsample) == 0) {
-                        const long long gp = (long long)tile * groups_per_tile + c0 / a.nsample;
-                        if (ch < L.c3 && gp * a.nsample < a.total_rows) {
-                            const float o = fmaxf(run + bias, 0.f);
-                            const long long cloud = gp / a.m, p = gp - cloud * a.m;
-                            a.out_cm[((size_t)cloud * a.ctot + a.coff + ch) * a.m + p] = o;
-                            if (a.out_pm) a.out_pm[(size_t)gp * a.ctot + a.coff + ch] = __float2half_rn(fminf(o, 65504.f));
-                        }
-                        run = -INFINITY;
-                    }
+                    for (int i = 0; i < 4; ++i)
+                        h[i] = pack_relu_f16x2(v[8 * q + 2 * i] + bias[16 * u + 8 * q + 2 * i], v[8 * q + 2 * i + 1] + bias[16 * u + 8 * q + 2 * i + 1]);
+                    hd[(size_t)(2 * u + q) * TILE_M + row] = make_uint4(h[0], h[1], h[2], h[3]);
                 }
             }
+        };
+        // centroid gp = gp0 + g of this tile; (cloud, p) of gp0 is divided out once per tile, then walked
+        // Channel-major fp32 output: with lane = channel a direct store would touch 32 different sectors per instruction
+        // (4 useful bytes each).  When it fits, the batch's (channel x centroid) block is staged in the H buffers (free
+        // during epilogue 3) and written out with lanes along the centroid index: 64-128 contiguous bytes per channel.
+        const int GS = L.tb * groups_per_tile;                   // centroids per batch
+        const bool staged = (size_t)L.c3 * (GS + 1) * 4 <= (size_t)L.tb * L.h_bytes && GS >= 8;
+        float* stage = reinterpret_cast<float*>(hbuf);
+        unsigned e_gp0 = 0, e_cloud0 = 0, e_p0 = 0;
+        int e_bi = 0;
+        auto emit = [&](int ch, int g, float mx, float bias) {
+            const unsigned gp = e_gp0 + (unsigned)g;
+            if (ch < L.c3 && (gp << a.lg_ns) < (unsigned)a.total_rows) {
+                const float o = fmaxf(mx + bias, 0.f);
+                if (staged) stage[ch * (GS + 1) + e_bi * groups_per_tile + g] = o;
+                else {
+                    unsigned cloud = e_cloud0, p = e_p0 + (unsigned)g;
+                    while (p >= (unsigned)a.m) { p -= (unsigned)a.m; ++cloud; }
+                    a.out_cm[((size_t)cloud * a.ctot + a.coff + ch) * a.m + p] = o;
+                }
+                if (a.out_pm) a.out_pm[(size_t)gp * a.ctot + a.coff + ch] = __float2half_rn(fminf(o, 65504.f));
+            }
+        };
+        auto set_tile = [&](int tile) {
+            e_gp0 = (unsigned)tile * (unsigned)groups_per_tile;
+            e_cloud0 = e_gp0 / (unsigned)a.m;
+            e_p0 = e_gp0 - e_cloud0 * (unsigned)a.m;
+        };
+        // 64 consecutive positions (columns) of channel block j of tile bi: neighbourhood max + emit
+        auto max_emit64 = [&](int bi, int tile, int j, int colhalf) {
+            const int ch = j * 128 + row;
+            const float bias = b3[ch];
+            float v[64];
+            tmem_ld_cols<4>(lane_taddr + bi * L.cstride + j * 128 + 64 * colhalf, v);
+            set_tile(tile); e_bi = bi;
+            const int gp0 = (64 * colhalf) >> a.lg_ns;
+            if (a.nsample == 8) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    float mx = v[8 * g];
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[8 * g + i]);
+                    emit(ch, gp0 + g, mx, bias);
+                }
+            } else if (a.nsample == 16) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float mx = v[16 * g];
+#pragma unroll
+                    for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[16 * g + i]);
+                    emit(ch, gp0 + g, mx, bias);
+                }
+            } else if (a.nsample == 32) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    float mx = v[32 * g];
+#pragma unroll
+                    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[32 * g + i]);
+                    emit(ch, gp0 + g, mx, bias);
+                }
+            } else {
+                float mx = v[0];
+#pragma unroll
+                for (int i = 1; i < 64; ++i) mx = fmaxf(mx, v[i]);
+                emit(ch, gp0, mx, bias);
+            }
+        };
+        auto max_emit128 = [&](int bi, int tile, int j) {            // nsample == 128: one neighbourhood per tile
+            const int ch = j * 128 + row;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float v[64];
+                tmem_ld_cols<4>(lane_taddr + bi * L.cstride + j * 128 + 64 * hh, v);
+#pragma unroll
+                for (int i = 0; i < 64; ++i) mx = fmaxf(mx, v[i]);
+            }
+            set_tile(tile); e_bi = bi;
+            emit(ch, 0, mx, b3[ch]);
+        };
+        const int t_first = split_cols ? 0 : half, t_step = split_cols ? 1 : 2;
+        for (long long tl = (long long)blockIdx.x * L.tb; tl < a.ntiles; tl += (long long)gridDim.x * L.tb) {
+            const int nb = (int)((a.ntiles - tl) < L.tb ? (a.ntiles - tl) : L.tb);
+            // ---- epilogue 1: D1 -> bias + ReLU -> fp16 -> H
+            mbar_wait(bar_dfull, nd & 1); ++nd;
+            tc_fence_after();
+            for (int bi = t_first; bi < nb; bi += t_step) relu_to_h(bi, L.c1, b1);
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_epi);
+            // ---- epilogue 2 (H1 is dead: MMA 2 has completed when d_full fires)
+            mbar_wait(bar_dfull, nd & 1); ++nd;
+            tc_fence_after();
+            for (int bi = t_first; bi < nb; bi += t_step) relu_to_h(bi, L.c2, b2);
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_epi);
+            // ---- epilogue 3: lane = output channel; max over each neighbourhood's nsample consecutive columns
+            mbar_wait(bar_dfull, nd & 1); ++nd;
+            tc_fence_after();
+            if (split_cols) {
+                if (a.nsample <= 64) { for (int j = 0; j < L.nb3; ++j) max_emit64(0, (int)tl, j, half); }
+                else { for (int j = half; j < L.nb3; j += 2) max_emit128(0, (int)tl, j); }
+            } else {
+                for (int bi = t_first; bi < nb; bi += t_step)
+                    for (int j = 0; j < L.nb3; ++j) {
+                        if (a.nsample <= 64) { max_emit64(bi, (int)tl + bi, j, 0); max_emit64(bi, (int)tl + bi, j, 1); }
+                        else max_emit128(bi, (int)tl + bi, j);
+                    }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_epi);                  // TMEM drained: the next batch's layer 1 may start
+            if (staged) {
+                asm volatile("bar.sync 1, %0;" ::"n"(SA_EPI_WARPS * 32) : "memory");     // the 8 epilogue warps only
+                const unsigned gpb = (unsigned)tl * (unsigned)groups_per_tile;            // first centroid of the batch
+                const unsigned cloudb = gpb / (unsigned)a.m, pb = gpb - cloudb * (unsigned)a.m;
+                const int G = nb * groups_per_tile;
+                const int et = warp * 32 + lane;                  // 0..255
+                for (int i = et; i < L.c3 * G; i += SA_EPI_WARPS * 32) {
+                    const int ch = i / G, g = i - ch * G;
+                    if (((gpb + (unsigned)g) << a.lg_ns) < (unsigned)a.total_rows) {
+                        unsigned cloud = cloudb, pp = pb + (unsigned)g;
+                        while (pp >= (unsigned)a.m) { pp -= (unsigned)a.m; ++cloud; }
+                        a.out_cm[((size_t)cloud * a.ctot + a.coff + ch) * a.m + pp] = stage[ch * (GS + 1) + g];
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(SA_EPI_WARPS * 32) : "memory");     // staging area is H again
+            }
         }
-        tc_fence_before();
-        __syncthreads();     // TMEM and act are free for the next tile
     }
 
     tc_fence_before();
@@ -358,13 +582,14 @@ G4D_API int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int
     if (b == 0 || m == 0) return 0;
     if (!params_dev || !xyz || !new_xyz || !idx || !out_cm || (d->c_in > 0 && !feat_pm)) return bad_arg("sa_mlp_max: null pointer");
     if (out_c_off < 0 || out_c_off + d->c3 > out_c_total) return bad_arg("sa_mlp_max: channel window outside the output");
-    if ((long long)b * n > 0xFFFFFFFEll) return bad_arg("sa_mlp_max: b*n exceeds 32-bit point ids");
     if (((uintptr_t)params_dev & 15) || ((uintptr_t)feat_pm & 15)) return bad_arg("sa_mlp_max: params/feat_pm must be 16-byte aligned");
     a.c_in = d->c_in; a.nsample = d->nsample; a.n = n; a.m = m;
-    a.total_rows = (long long)b * m * d->nsample;
-    const long long nt = (a.total_rows + TILE_M - 1) / TILE_M;
-    if (nt > INT32_MAX) return bad_arg("sa_mlp_max: too many tiles");
-    a.ntiles = (int)nt;
+    const long long rows = (long long)b * m * d->nsample;
+    if (rows > 0x7FFFFF00ll) return bad_arg("sa_mlp_max: b*m*nsample must stay below 2^31");
+    a.total_rows = (int)rows;
+    a.ntiles = (int)((rows + TILE_M - 1) / TILE_M);
+    a.lg_ns = 0; while ((1 << a.lg_ns) < d->nsample) ++a.lg_ns;
+    a.lg_tb = 0; while ((1 << a.lg_tb) < a.L.tb) ++a.lg_tb;
     a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.feat_pm = (const __half*)feat_pm;
     a.params = (const unsigned char*)params_dev;
     a.out_cm = out_cm; a.out_pm = (__half*)out_pm; a.ctot = out_c_total; a.coff = out_c_off;
@@ -372,14 +597,15 @@ G4D_API int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int
     cudaError_t e = cudaFuncSetAttribute(sa_mlp_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
     if (e != cudaSuccess) { set_error("sa_mlp_max: shared memory opt-in (%u B): %s", a.L.total_smem, cudaGetErrorString(e)); return (int)e; }
     cudaFuncSetAttribute(sa_mlp_max_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    // resident CTAs per SM: shared memory (227 KB usable, 1 KB reserved per CTA), TMEM columns (512 per SM), warps
+    // resident CTAs per SM: shared memory (227 KB usable, 1 KB reserved per CTA), TMEM columns (512 per SM), threads
     int occ = (int)((227u * 1024u) / (a.L.total_smem + 1024u));
     const int tmem_limit = 512 / (int)a.L.tmem_cols;
     if (occ > tmem_limit) occ = tmem_limit;
-    if (occ > 8) occ = 8;
+    if (occ > 2048 / SA_THREADS) occ = 2048 / SA_THREADS;
     if (occ < 1) occ = 1;
     long long grid = (long long)sm_count() * occ;
-    if (grid > a.ntiles) grid = a.ntiles;
+    const long long nbatches = (a.ntiles + a.L.tb - 1) / a.L.tb;
+    if (grid > nbatches) grid = nbatches;
     sa_mlp_max_kernel<<<(unsigned)grid, SA_THREADS, a.L.total_smem, (cudaStream_t)stream>>>(a);
     return finish_launch("g4d sa_mlp_max");
 }

@@ -216,4 +216,22 @@ class PointnetFPModule(nn.Module):
             new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
         else:
             new_features = interpolated_feats
+        folded = self._folded_mlp(new_features)
+        if folded is not None:
+            # eval mode, no autograd: BatchNorm folded into the 1x1 convolutions -> conv(+bias) and in-place ReLU per layer
+            y = new_features.unsqueeze(-1)
+            for w, b in folded:
+                y = F.relu_(F.conv2d(y, w, b))
+            return y.squeeze(-1)
         return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+
+    def _folded_mlp(self, x):
+        if self.training or not x.is_cuda or (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.mlp.parameters()))):
+            return None
+        ver = pt_utils.shared_mlp_version(self.mlp)
+        hit = getattr(self, "_fold_cache", None)
+        if hit is None or hit[0] != ver:
+            f = pt_utils.fold_shared_mlp(self.mlp)
+            hit = (ver, None if f is None else [(w[:, :, None, None].contiguous(), b) for w, b in f])
+            self._fold_cache = hit
+        return hit[1]
