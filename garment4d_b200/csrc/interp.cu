@@ -119,3 +119,53 @@ G4D_API int g4d_three_interpolate_grad(int b, int c, int n, int m, const float* 
     three_interpolate_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, m, grad_out, idx, weight, grad_points);
     return finish_launch("g4d three_interpolate_grad");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// y[b,c,:] = max(y[b,c,:] + bias[c], 0) in place, one pass (channel-major (b,c,n)).  Epilogue of the feature-propagation
+// 1x1 convolutions that stay on the library GEMM (eval-mode BatchNorm folded into weight/bias): replaces the separate
+// bias-add and ReLU passes torch issues after cudnn/cutlass convolutions.
+namespace g4d {
+__global__ void __launch_bounds__(256)
+bias_relu_kernel(int c, long long n4, int relu, float4* __restrict__ y, const float* __restrict__ bias) {
+    const long long row = blockIdx.y;                     // b * c + channel
+    const float bv = __ldg(bias + (int)(row % c));
+    float4* p = y + row * n4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = p[i];
+        v.x += bv; v.y += bv; v.z += bv; v.w += bv;
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        p[i] = v;
+    }
+}
+__global__ void bias_relu_scalar_kernel(int c, long long n, int relu, float* __restrict__ y, const float* __restrict__ bias) {
+    const long long row = blockIdx.y;
+    const float bv = __ldg(bias + (int)(row % c));
+    float* p = y + row * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = p[i] + bv;
+        p[i] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+}  // namespace g4d
+
+G4D_API int g4d_bias_relu_inplace(int b, int c, long long n, float* y, const float* bias, int relu, void* stream) {
+    if (b < 0 || c < 0 || n < 0) return bad_arg("bias_relu_inplace: negative size");
+    if (b == 0 || c == 0 || n == 0) return 0;
+    if (!y || !bias) return bad_arg("bias_relu_inplace: null pointer");
+    if ((long long)b * c > 65535ll * 32768ll) return bad_arg("bias_relu_inplace: too many rows");
+    const long long rows = (long long)b * c;
+    if (rows > 2147483647ll) return bad_arg("bias_relu_inplace: too many rows");
+    if (n % 4 == 0 && ((uintptr_t)y & 15) == 0) {
+        const long long n4 = n / 4;
+        dim3 grid((unsigned)((n4 + 255) / 256 > 64 ? 64 : (n4 + 255) / 256), (unsigned)rows);
+        if (rows > 65535) { // fold rows into x when the y-dimension would overflow
+            return bad_arg("bias_relu_inplace: b*c > 65535 rows not supported");
+        }
+        g4d::bias_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n4, relu, (float4*)y, bias);
+    } else {
+        if (rows > 65535) return bad_arg("bias_relu_inplace: b*c > 65535 rows not supported");
+        dim3 grid((unsigned)((n + 255) / 256 > 64 ? 64 : (n + 255) / 256), (unsigned)rows);
+        g4d::bias_relu_scalar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, relu, y, bias);
+    }
+    return finish_launch("g4d bias_relu_inplace");
+}

@@ -219,10 +219,17 @@ class PointnetFPModule(nn.Module):
         folded = self._folded_mlp(new_features)
         if folded is not None:
             # eval mode, no autograd: BatchNorm folded into the 1x1 convolutions -> conv(+bias) and in-place ReLU per layer
-            y = new_features.unsqueeze(-1)
+            # eval mode: library GEMM (1x1 conv, no bias) + ONE in-place bias+ReLU pass of ours per layer
+            y = new_features
+            L = _lib.lib()
             for w, b in folded:
-                y = F.relu_(F.conv2d(y, w, b))
-            return y.squeeze(-1)
+                y = F.conv2d(y.unsqueeze(-1), w).squeeze(-1)
+                if y.shape[0] * y.shape[1] <= 65535 and y.is_contiguous():
+                    rc = L.g4d_bias_relu_inplace(y.shape[0], y.shape[1], y.shape[2], _lib.ptr(y), _lib.ptr(b), 1, _lib.stream_ptr())
+                    _lib.check(rc, "g4d_bias_relu_inplace")
+                else:
+                    y = F.relu_(y + b[None, :, None])
+            return y
         return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
 
     def _folded_mlp(self, x):

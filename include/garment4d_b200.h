@@ -151,6 +151,10 @@ int g4d_fp_pack_params(const g4d_fp_desc* d, const float* w1, const float* b1, c
 int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int b, int n, int m, const float* dist2, const int* idx,
                       const void* known_pm, float* out_feat, float* out_head, void* stream);
 
+/* y[b,c,:] = max(y[b,c,:] + bias[c], 0) in place (relu = 0: bias only); channel-major (b,c,n), b*c <= 65535.  One-pass
+ * epilogue for the feature-propagation 1x1 convolutions that stay on the library GEMM (pointnet2_modules.py:154). */
+int g4d_bias_relu_inplace(int b, int c, long long n, float* y, const float* bias, int relu, void* stream);
+
 /* ---- 3. SMPL linear-blend skinning (smplx/smplx/lbs.py) ----------------------------------------- */
 
 /* batch_rodrigues (lbs.py:312-346): rot_vecs (n,3) -> rot_mats (n,3,3) */
