@@ -122,6 +122,22 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
     }
 }
 
+// Wait used by roles that are far off the critical path (producers waiting for a free ring slot): poll, then sleep.
+// A tight try_wait loop in 8 idle warps would take most of the SM's issue slots away from the epilogue warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -248,7 +264,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             if (nchunk_feat == 0) {
                 // xyz-only level: a single slice per tile
                 const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+                mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);
                 uint4* dst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
                 dst[r] = xc0;
                 dst[TILE_M + r] = xc1;
@@ -280,7 +296,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                     for (int e2 = 0; e2 < 4; ++e2) {
                         if (s0 + e2 < S) {                        // uniform
                             const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                            mbar_wait(bar_empty + 8 * slot, ph ^ 1);      // slot free (first lap passes at once)
+                            mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);   // slot free (first lap passes at once)
                             uint4* dst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
                             dst[r] = vc[2 * e2];
                             dst[TILE_M + r] = vc[2 * e2 + 1];
