@@ -211,6 +211,47 @@ query_and_group_kernel(int n, int m, int c, float radius2, int use_xyz, const fl
     }
 }
 
+// Grouping stage of QueryAndGroup alone, given idx: (3+C) x P x K tensor written once with 16-byte stores; each thread owns
+// 4 consecutive samples of one centroid (its 4 source indices stay in registers) and walks a slab of channels.
+// Replaces grouping_operation(xyz) -> subtract -> grouping_operation(features) -> cat (pointnet2_utils.py:251-258).
+constexpr int GF_CH_SLAB = 16;
+__global__ void __launch_bounds__(256)
+group_fused_kernel(int n, int m, int c, int K, int use_xyz, const float* __restrict__ xyz_all, const float* __restrict__ new_xyz_all,
+                   const float* __restrict__ feat_all, const int* __restrict__ idx_all, float* __restrict__ out_all) {
+    const size_t cloud = blockIdx.z;
+    const size_t plane = (size_t)m * K;                       // elements per channel plane (multiple of 4: K % 4 == 0)
+    const size_t e4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e4 * 4 >= plane) return;
+    const int4 id = __ldg(reinterpret_cast<const int4*>(idx_all + cloud * plane) + e4);
+    const int cxyz = use_xyz ? 3 : 0;
+    float* out = out_all + cloud * (size_t)(cxyz + c) * plane;
+    const int slab = blockIdx.y;
+    if (use_xyz && slab == 0) {
+        const float* xyz = xyz_all + cloud * (size_t)n * 3;
+        const float* q = new_xyz_all + (cloud * m + (e4 * 4) / K) * 3;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float qd = __ldg(q + d);
+            float4 v;
+            v.x = __ldg(xyz + 3 * id.x + d) - qd; v.y = __ldg(xyz + 3 * id.y + d) - qd;
+            v.z = __ldg(xyz + 3 * id.z + d) - qd; v.w = __ldg(xyz + 3 * id.w + d) - qd;
+            reinterpret_cast<float4*>(out + d * plane)[e4] = v;
+        }
+    }
+    if (c > 0) {
+        const float* feat = feat_all + cloud * (size_t)c * n;
+        float* of = out + cxyz * plane;
+        const int c0 = slab * GF_CH_SLAB, c1 = min(c, c0 + GF_CH_SLAB);
+#pragma unroll 4
+        for (int ci = c0; ci < c1; ++ci) {
+            const float* row = feat + (size_t)ci * n;
+            float4 v;
+            v.x = __ldg(row + id.x); v.y = __ldg(row + id.y); v.z = __ldg(row + id.z); v.w = __ldg(row + id.w);
+            reinterpret_cast<float4*>(of + (size_t)ci * plane)[e4] = v;
+        }
+    }
+}
+
 static inline dim3 chan_grid(int work, int c, int b) {
     // y = channel slabs: enough CTAs to fill the machine without one CTA per channel re-reading idx
     int y = c < 8 ? c : 8;
@@ -297,4 +338,22 @@ G4D_API int g4d_query_and_group(int b, int n, int m, int c, float radius, int ns
     }
 #undef G4D_QG
     return finish_launch("g4d query_and_group");
+}
+
+// Grouping stage of QueryAndGroup.forward (pointnet2_utils.py:251-258) from a given idx (b,m,nsample), nsample % 4 == 0:
+// out (b, 3+c, m, nsample) [use_xyz] or (b, c, m, nsample), one pass, 16-byte stores.
+G4D_API int g4d_group_fused(int b, int n, int m, int c, int nsample, int use_xyz, const float* xyz, const float* new_xyz,
+                            const float* features, const int* idx, float* out, void* stream) {
+    if (b < 0 || n <= 0 || m < 0 || c < 0 || nsample <= 0) return bad_arg("group_fused: bad size");
+    if (b == 0 || m == 0) return 0;
+    if (nsample % 4) return bad_arg("group_fused: nsample must be a multiple of 4");
+    if (!idx || !out || (use_xyz && (!xyz || !new_xyz)) || (c > 0 && !features)) return bad_arg("group_fused: null pointer");
+    if (c == 0 && !use_xyz) return bad_arg("group_fused: no features and use_xyz = 0");
+    if (((uintptr_t)idx & 15) || ((uintptr_t)out & 15)) return bad_arg("group_fused: idx/out must be 16-byte aligned");
+    const long long plane4 = (long long)m * nsample / 4;
+    int slabs = (c + GF_CH_SLAB - 1) / GF_CH_SLAB;
+    if (slabs < 1) slabs = 1;
+    dim3 grid((unsigned)((plane4 + 255) / 256), (unsigned)slabs, (unsigned)b);
+    group_fused_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, c, nsample, use_xyz, xyz, new_xyz, features, idx, out);
+    return finish_launch("g4d group_fused");
 }

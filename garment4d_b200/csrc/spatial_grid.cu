@@ -153,11 +153,28 @@ ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_x
         // sum, and all 32 lanes then walk the concatenation.
         int beg = 0, len = 0;
         if (lane < 9) {
-            const int zz = cz + lane / 3 - 1, yy = cy + lane % 3 - 1;
+            const int oz = lane / 3 - 1, oy = lane % 3 - 1;
+            const int zz = cz + oz, yy = cy + oy;
             if (zz >= 0 && zz < H.dz && yy >= 0 && yy < H.dy) {
-                const int row = (zz * H.dy + yy) * H.dx;
-                beg = __ldg(cell_start + row + x0);
-                len = __ldg(cell_start + row + x1 + 1) - beg;
+                // Conservative culling against the larger radius: gap from the query to the neighbouring row of cells
+                // (0 for the query's own row; computed from the same cell faces the point binning used, 0.1 % slack).
+                const float fy0 = H.oy + (float)cy * H.h, fz0 = H.oz + (float)cz * H.h, fx0 = H.ox + (float)cx * H.h;
+                const float gy = oy < 0 ? qy - fy0 : (oy > 0 ? (fy0 + H.h) - qy : 0.f);
+                const float gz = oz < 0 ? qz - fz0 : (oz > 0 ? (fz0 + H.h) - qz : 0.f);
+                const float gyp = fmaxf(gy, 0.f), gzp = fmaxf(gz, 0.f);
+                const float rem = r2max * 1.001f - gyp * gyp - gzp * gzp;
+                if (rem >= 0.f && H.inv_h > 0.f) {
+                    const float gxl = fmaxf(qx - fx0, 0.f), gxr = fmaxf((fx0 + H.h) - qx, 0.f);
+                    const int xa = (gxl * gxl > rem) ? cx : x0;          // left neighbour cell cannot hold a hit
+                    const int xb = (gxr * gxr > rem) ? cx : x1;
+                    const int row = (zz * H.dy + yy) * H.dx;
+                    beg = __ldg(cell_start + row + xa);
+                    len = __ldg(cell_start + row + xb + 1) - beg;
+                } else if (H.inv_h == 0.f) {                             // degenerate single-cell grid: everything is a candidate
+                    const int row = (zz * H.dy + yy) * H.dx;
+                    beg = __ldg(cell_start + row + x0);
+                    len = __ldg(cell_start + row + x1 + 1) - beg;
+                }
             }
         }
         for (int r = 0; r < 9; ++r) {
@@ -179,9 +196,19 @@ ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_x
         for (int s = 0; s < NS; ++s) {
             const int K = KK[s];
             int* row = outs[s] + (size_t)q * K;
-            // each lane owns wpl consecutive words; exclusive prefix of popcounts across lanes
+            // each lane owns wpl consecutive words (held in registers when wpl == 8, i.e. n <= 8192, the hot case)
+            unsigned wreg[8];
             int cnt = 0;
-            for (int w = 0; w < wpl; ++w) { const int wi = lane * wpl + w; if (wi < nwords) cnt += __popc(bm[s][wi]); }
+            if (wpl == 8 && nwords == 256) {
+                const uint4 a4 = reinterpret_cast<const uint4*>(bm[s])[lane * 2], b4 = reinterpret_cast<const uint4*>(bm[s])[lane * 2 + 1];
+                wreg[0] = a4.x; wreg[1] = a4.y; wreg[2] = a4.z; wreg[3] = a4.w; wreg[4] = b4.x; wreg[5] = b4.y; wreg[6] = b4.z; wreg[7] = b4.w;
+                reinterpret_cast<uint4*>(bm[s])[lane * 2] = make_uint4(0, 0, 0, 0);          // ready for the next query
+                reinterpret_cast<uint4*>(bm[s])[lane * 2 + 1] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int w = 0; w < 8; ++w) cnt += __popc(wreg[w]);
+            } else {
+                for (int w = 0; w < wpl; ++w) { const int wi = lane * wpl + w; if (wi < nwords) cnt += __popc(bm[s][wi]); }
+            }
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
@@ -189,21 +216,34 @@ ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_x
             if (total > 0) {       // rows without any hit are left untouched (ball_query_gpu.cu: idx stays as the caller zero-filled it)
                 int rank = incl - cnt;
                 int first_local = 0x7FFFFFFF;
-                for (int w = 0; w < wpl; ++w) {
-                    const int wi = lane * wpl + w;
-                    if (wi >= nwords) break;
-                    unsigned bits = bm[s][wi];
-                    if (bits && first_local == 0x7FFFFFFF) first_local = wi * 32 + __ffs(bits) - 1;
-                    while (bits && rank < K) {
-                        const int b = __ffs(bits) - 1;
-                        row[rank++] = wi * 32 + b;
-                        bits &= bits - 1;
+                if (wpl == 8 && nwords == 256) {
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        unsigned bits = wreg[w];
+                        const int wi = lane * 8 + w;
+                        if (bits && first_local == 0x7FFFFFFF) first_local = wi * 32 + __ffs(bits) - 1;
+                        while (bits && rank < K) {
+                            row[rank++] = wi * 32 + __ffs(bits) - 1;
+                            bits &= bits - 1;
+                        }
+                    }
+                } else {
+                    for (int w = 0; w < wpl; ++w) {
+                        const int wi = lane * wpl + w;
+                        if (wi >= nwords) break;
+                        unsigned bits = bm[s][wi];
+                        if (bits && first_local == 0x7FFFFFFF) first_local = wi * 32 + __ffs(bits) - 1;
+                        while (bits && rank < K) {
+                            row[rank++] = wi * 32 + __ffs(bits) - 1;
+                            bits &= bits - 1;
+                        }
                     }
                 }
                 const int first = __reduce_min_sync(0xFFFFFFFFu, first_local);
                 for (int p = total + lane; p < K; p += 32) row[p] = first;
             }
-            for (int w = 0; w < wpl; ++w) { const int wi = lane * wpl + w; if (wi < nwords) bm[s][wi] = 0u; }
+            if (!(wpl == 8 && nwords == 256))
+                for (int w = 0; w < wpl; ++w) { const int wi = lane * wpl + w; if (wi < nwords) bm[s][wi] = 0u; }
         }
         __syncwarp();
     }

@@ -285,11 +285,18 @@ class _QueryAndGroupFused(Function):
         P = new_xyz.size(1)
         C = 0 if features is None else features.size(1)
         cout = (3 if use_xyz else 0) + C
-        idx = _i32(B, P, nsample, device=xyz.device)
         out = _f32(B, cout, P, nsample, device=xyz.device)
-        rc = _lib.lib().g4d_query_and_group(B, N, P, C, float(radius), nsample, int(use_xyz), _lib.ptr(xyz), _lib.ptr(new_xyz),
+        if nsample % 4 == 0:
+            # ball query (uniform grid for large clouds), then ONE grouping pass (16-byte stores) for xyz, features and the cat
+            idx = BallQuery.apply(radius, nsample, xyz, new_xyz)
+            rc = _lib.lib().g4d_group_fused(B, N, P, C, nsample, int(use_xyz), _lib.ptr(xyz), _lib.ptr(new_xyz),
                                             _lib.ptr(features), _lib.ptr(idx), _lib.ptr(out), _lib.stream_ptr())
-        _lib.check(rc, "g4d_query_and_group")
+            _lib.check(rc, "g4d_group_fused")
+        else:
+            idx = _i32(B, P, nsample, device=xyz.device)
+            rc = _lib.lib().g4d_query_and_group(B, N, P, C, float(radius), nsample, int(use_xyz), _lib.ptr(xyz), _lib.ptr(new_xyz),
+                                                _lib.ptr(features), _lib.ptr(idx), _lib.ptr(out), _lib.stream_ptr())
+            _lib.check(rc, "g4d_query_and_group")
         ctx.meta = (idx, N, C, use_xyz)
         return out
 

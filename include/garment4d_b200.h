@@ -91,6 +91,11 @@ int g4d_ball_query2(int b, int n, int m, float radius0, int nsample0, int* idx0,
 int g4d_query_and_group(int b, int n, int m, int c, float radius, int nsample, int use_xyz, const float* xyz,
                         const float* new_xyz, const float* features, int* idx, float* out, void* stream);
 
+/* Grouping stage of QueryAndGroup alone, from a given idx (b,m,nsample), nsample % 4 == 0: group(xyz) - centroid,
+ * group(features) and the concatenation in one write pass (pointnet2_utils.py:251-258).  out as g4d_query_and_group. */
+int g4d_group_fused(int b, int n, int m, int c, int nsample, int use_xyz, const float* xyz, const float* new_xyz,
+                    const float* features, const int* idx, float* out, void* stream);
+
 /* Uniform-grid acceleration of the neighbour searches; results identical to the brute-force entry points above.
  * g4d_grid_build sorts each cloud's points by cell (cell edge >= min_cell, grown until <= 4096 cells; min_cell <= -1:
  * automatic, -min_cell cells along the longest axis).  grid: device buffer of g4d_grid_bytes(b,n), 16-byte aligned. */
