@@ -253,11 +253,10 @@ ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_x
 // three nearest neighbours through a grid over the KNOWN points.  order (optional): processing order of the
 // unknown points (the 'k' column of a grid built over them) so that the threads of a warp are spatial neighbours.
 
-__device__ __forceinline__ void nn3_insert(float d, int k, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
-    // total order (d, k): identical to the reference's strict '<' insertion while scanning k upwards
-    if (d < b1 || (d == b1 && k < i1)) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
-    else if (d < b2 || (d == b2 && k < i2)) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
-    else if (d < b3 || (d == b3 && k < i3)) { b3 = d; i3 = k; }
+// (d, k) packed as one 64-bit key: d >= 0, so its float bits order like the value and "smaller key" == the reference's
+// strict '<' insertion while scanning k upwards (ties: lower index first).  NaN distances sort above +inf: never kept.
+__device__ __forceinline__ unsigned long long nn_key(float d, int k) {
+    return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)k;
 }
 
 __global__ void __launch_bounds__(256)
@@ -275,15 +274,23 @@ three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const 
     const float* u = unknown_all + (cloud * n + pt) * 3;
     const float ux = __ldg(u), uy = __ldg(u + 1), uz = __ldg(u + 2);
     const int cx = cell_coord(ux, H.ox, H.inv_h, H.dx), cy = cell_coord(uy, H.oy, H.inv_h, H.dy), cz = cell_coord(uz, H.oz, H.inv_h, H.dz);
-    float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
-    int i1 = 0, i2 = 0, i3 = 0;
-    // when fewer than 3 candidates exist the reference leaves index 0 / distance 1e40 -> inf: (inf, 0) entries; a real
-    // candidate with k = 0 and finite d always beats them, and d == inf candidates never insert in the reference either.
+    // fewer than 3 known points: the reference leaves distance 1e40 -> (float) inf and index 0 in the unused places
+    const unsigned long long EMPTY = 0x7F80000000000000ull;
+    unsigned long long k1 = EMPTY, k2 = EMPTY, k3 = EMPTY;
+    // own-cell faces, for the per-row lower bounds
+    const float fx0 = H.ox + (float)cx * H.h, fy0 = H.oy + (float)cy * H.h, fz0 = H.oz + (float)cz * H.h;
     const int maxring = max(max(max(cx, H.dx - 1 - cx), max(cy, H.dy - 1 - cy)), max(cz, H.dz - 1 - cz));
     for (int R = 0; R <= maxring; ++R) {
         for (int zz = max(cz - R, 0); zz <= min(cz + R, H.dz - 1); ++zz) {
             const bool zshell = (zz == cz - R) || (zz == cz + R);
+            // distance from the query to the slab of cells zz (0 inside the query's own slab; conservative when clamped)
+            const float gz = zz < cz ? fmaxf(uz - (fz0 - (float)(cz - zz - 1) * H.h), 0.f) : (zz > cz ? fmaxf((fz0 + (float)(zz - cz) * H.h) - uz, 0.f) : 0.f);
             for (int yy = max(cy - R, 0); yy <= min(cy + R, H.dy - 1); ++yy) {
+                const float gy = yy < cy ? fmaxf(uy - (fy0 - (float)(cy - yy - 1) * H.h), 0.f) : (yy > cy ? fmaxf((fy0 + (float)(yy - cy) * H.h) - uy, 0.f) : 0.f);
+                // every point of this row of cells is at least sqrt(gy^2 + gz^2) away: skip it when that cannot beat the
+                // current third best (0.998: slack for the rounding of cell faces / binning)
+                const float b3 = __uint_as_float((unsigned)(k3 >> 32));
+                if ((gy * gy + gz * gz) * 0.998f > b3) continue;
                 const bool full = zshell || (yy == cy - R) || (yy == cy + R);
                 const int row = (zz * H.dy + yy) * H.dx;
                 // full row of the shell: one contiguous run; otherwise only the two end cells x = cx-R and x = cx+R
@@ -291,12 +298,16 @@ three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const 
                 for (int sgm = 0; sgm < nseg; ++sgm) {
                     int xa, xb;
                     if (full) { xa = max(cx - R, 0); xb = min(cx + R, H.dx - 1); }
-                    else { xa = xb = (sgm == 0 ? cx - R : cx + R); if (xa < 0 || xa >= H.dx || (sgm == 1 && R == 0)) continue; }
+                    else { xa = xb = (sgm == 0 ? cx - R : cx + R); if (xa < 0 || xa >= H.dx) continue; }
                     const int beg = __ldg(cell_start + row + xa), end = __ldg(cell_start + row + xb + 1);
                     for (int j = beg; j < end; ++j) {
                         const float4 p = __ldg(sorted + j);
-                        const float d = sqdist_ref(ux - p.x, uy - p.y, uz - p.z);
-                        if (d < b3 || (d == b3 && __float_as_int(p.w) < i3)) nn3_insert(d, __float_as_int(p.w), b1, b2, b3, i1, i2, i3);
+                        const unsigned long long key = nn_key(sqdist_ref(ux - p.x, uy - p.y, uz - p.z), __float_as_int(p.w));
+                        if (key < k3) {
+                            k3 = key;
+                            if (k3 < k2) { const unsigned long long tmp = k2; k2 = k3; k3 = tmp; }
+                            if (k2 < k1) { const unsigned long long tmp = k1; k1 = k2; k2 = tmp; }
+                        }
                     }
                 }
             }
@@ -305,19 +316,19 @@ three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const 
         // the grid continues; its distance is at least the gap from the query to that face.  0.998 keeps the stop
         // test conservative under rounding of the cell assignment and of these face coordinates.
         float bound = INFINITY;
-        if (cx - R > 0) bound = fminf(bound, ux - (H.ox + (float)(cx - R) * H.h));
-        if (cx + R < H.dx - 1) bound = fminf(bound, (H.ox + (float)(cx + R + 1) * H.h) - ux);
-        if (cy - R > 0) bound = fminf(bound, uy - (H.oy + (float)(cy - R) * H.h));
-        if (cy + R < H.dy - 1) bound = fminf(bound, (H.oy + (float)(cy + R + 1) * H.h) - uy);
-        if (cz - R > 0) bound = fminf(bound, uz - (H.oz + (float)(cz - R) * H.h));
-        if (cz + R < H.dz - 1) bound = fminf(bound, (H.oz + (float)(cz + R + 1) * H.h) - uz);
+        if (cx - R > 0) bound = fminf(bound, ux - (fx0 - (float)R * H.h));
+        if (cx + R < H.dx - 1) bound = fminf(bound, (fx0 + (float)(R + 1) * H.h) - ux);
+        if (cy - R > 0) bound = fminf(bound, uy - (fy0 - (float)R * H.h));
+        if (cy + R < H.dy - 1) bound = fminf(bound, (fy0 + (float)(R + 1) * H.h) - uy);
+        if (cz - R > 0) bound = fminf(bound, uz - (fz0 - (float)R * H.h));
+        if (cz + R < H.dz - 1) bound = fminf(bound, (fz0 + (float)(R + 1) * H.h) - uz);
         bound = fmaxf(bound, 0.f);
-        if (b3 < bound * bound * 0.998f) break;
+        if (__uint_as_float((unsigned)(k3 >> 32)) < bound * bound * 0.998f) break;
     }
     float* od = dist2_all + (cloud * n + pt) * 3;
     int* oi = idx_all + (cloud * n + pt) * 3;
-    od[0] = b1; od[1] = b2; od[2] = b3;
-    oi[0] = i1; oi[1] = i2; oi[2] = i3;
+    od[0] = __uint_as_float((unsigned)(k1 >> 32)); od[1] = __uint_as_float((unsigned)(k2 >> 32)); od[2] = __uint_as_float((unsigned)(k3 >> 32));
+    oi[0] = (int)(unsigned)k1; oi[1] = (int)(unsigned)k2; oi[2] = (int)(unsigned)k3;
 }
 
 }  // namespace g4d
