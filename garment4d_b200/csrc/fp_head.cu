@@ -150,8 +150,8 @@ fp_interp_mlp_kernel(const FpArgs a) {
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const long long R = (long long)tile * FP_TILE + tid;
         const bool live = R < a.total_rows;
-        const long long cloud = live ? R / a.n : 0;
-        const int pt = live ? (int)(R - cloud * a.n) : 0;
+        const unsigned cloud = live ? (unsigned)((unsigned long long)R / (unsigned)a.n) : 0u;   // total_rows < 2^32 * n: one 64/32 division
+        const int pt = live ? (int)(R - (long long)cloud * a.n) : 0;
         // ---- interpolation weights, exactly the reference's torch arithmetic (pointnet2_modules.py:141-143) ----
         {
             uint32_t p0 = 0xFFFFFFFFu, p1 = 0xFFFFFFFFu, p2 = 0xFFFFFFFFu;
@@ -164,7 +164,7 @@ fp_interp_mlp_kernel(const FpArgs a) {
                 const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 2)), 1e-8f));
                 const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
                 w0 = __fdiv_rn(r0, norm); w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm);
-                const uint32_t base = (uint32_t)(cloud * a.m);
+                const uint32_t base = cloud * (uint32_t)a.m;
                 p0 = base + (uint32_t)__ldg(id); p1 = base + (uint32_t)__ldg(id + 1); p2 = base + (uint32_t)__ldg(id + 2);
             }
             rowpt[tid] = p0; rowpt[FP_TILE + tid] = p1; rowpt[2 * FP_TILE + tid] = p2;
@@ -182,18 +182,30 @@ fp_interp_mlp_kernel(const FpArgs a) {
                 const uint4* s0 = reinterpret_cast<const uint4*>(a.known_pm + (size_t)q0 * L.c_in);
                 const uint4* s1 = reinterpret_cast<const uint4*>(a.known_pm + (size_t)q1 * L.c_in);
                 const uint4* s2 = reinterpret_cast<const uint4*>(a.known_pm + (size_t)q2 * L.c_in);
-                for (int c = cl; c < nchunk; c += 4) {
-                    uint4 o = make_uint4(0, 0, 0, 0);
-                    if (q0 != 0xFFFFFFFFu) {
-                        float f0[8], f1[8], f2[8];
-                        unpack8(__ldg(s0 + c), f0); unpack8(__ldg(s1 + c), f1); unpack8(__ldg(s2 + c), f2);
-                        float r[8];
+                // 4 chunks per lane at a time: all 12 loads (3 taps x 4 chunks) are issued before the first use
+                for (int cb = cl; cb < nchunk; cb += 16) {
+                    uint4 l0[4], l1[4], l2[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)     // interpolate_gpu.cu:96 in the reference build's order
-                            r[i] = __fmaf_rn(w2, f2[i], __fmaf_rn(w0, f0[i], __fmul_rn(w1, f1[i])));
-                        o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = cb + 4 * u;
+                        l0[u] = l1[u] = l2[u] = make_uint4(0, 0, 0, 0);
+                        if (c < nchunk && q0 != 0xFFFFFFFFu) { l0[u] = __ldg(s0 + c); l1[u] = __ldg(s1 + c); l2[u] = __ldg(s2 + c); }
                     }
-                    dst[(size_t)c * FP_TILE + row] = o;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = cb + 4 * u;
+                        if (c < nchunk) {
+                            float f0[8], f1[8], f2[8], r[8];
+                            unpack8(l0[u], f0); unpack8(l1[u], f1); unpack8(l2[u], f2);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)     // interpolate_gpu.cu:96 in the reference build's order
+                                r[i] = __fmaf_rn(w2, f2[i], __fmaf_rn(w0, f0[i], __fmul_rn(w1, f1[i])));
+                            uint4 o = make_uint4(0, 0, 0, 0);
+                            if (q0 != 0xFFFFFFFFu)
+                                o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
+                            dst[(size_t)c * FP_TILE + row] = o;
+                        }
+                    }
                 }
             }
         }

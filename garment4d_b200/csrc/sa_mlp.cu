@@ -158,6 +158,7 @@ struct SaMlpArgs {
     float* out_cm;                   // (b, ctot, m)
     __half* out_pm;                  // (b, m, ctot) or null
     int ctot, coff;
+    long long* dbg;                  // optional timeline buffer (g4d_debug_timeline), CTA 0 only
 };
 
 __global__ void __launch_bounds__(SA_THREADS)
@@ -272,42 +273,53 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_full + 8 * slot);
             } else {
-                const uint4* srcrow = reinterpret_cast<const uint4*>(a.feat_pm + (size_t)pt * a.c_in);
-                uint4 vc[8], vn[8];
+                // Feature levels: every 16-byte chunk of the neighbour's fp16 row goes global -> shared with cp.async (LDGSTS), one
+                // commit group per K-slice, ALL slices of the tile in flight at once (no register staging: 128 threads x 2S copies
+                // = the whole 128 x k0 tile outstanding, which is what hides the L2/HBM latency of the gather); then the slices are
+                // handed to the MMA warp in order as their groups complete.
+                const char* srcrow = reinterpret_cast<const char*>(a.feat_pm + (size_t)pt * a.c_in);
+                // (waves of at most min(S, RING) slices: a wave must fit the ring, or waiting for its own slots would deadlock)
+                const int wave = S < RING ? S : RING;
+                for (int w0 = 0; w0 < S; w0 += wave) {
+                const int w1 = (w0 + wave < S) ? w0 + wave : S;
+                for (int sl = w0; sl < w1; ++sl) {
+                    const uint32_t slot = (it + sl) % RING, ph = ((it + sl) / RING) & 1;
+                    mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);           // slot free (first lap passes at once)
+                    const uint32_t sdst = s_ring + slot * SLICE_BYTES + (uint32_t)r * 16;
+                    uint4* gdst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    vc[e] = make_uint4(0, 0, 0, 0);
-                    if (e < nchunk_feat) { if (live) vc[e] = __ldg(srcrow + e); }
-                    else if (e == nchunk_feat) vc[e] = xc0;
-                    else if (e == nchunk_feat + 1) vc[e] = xc1;
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = 2 * sl + h;                               // 16-byte chunk index along K
+                        if (c < nchunk_feat)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + h * TILE_M * 16), "l"(srcrow + (size_t)c * 16),
+                                         "r"(live ? 16 : 0) : "memory");
+                        else gdst[h * TILE_M + r] = (c == nchunk_feat) ? xc0 : ((c == nchunk_feat + 1) ? xc1 : make_uint4(0, 0, 0, 0));
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
                 }
-                for (int s0 = 0; s0 < S; s0 += 4) {
-                    if (s0 + 4 < S) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int c = ((s0 + 4) << 1) + e;    // 16-byte chunk index along K
-                            vn[e] = make_uint4(0, 0, 0, 0);
-                            if (c < nchunk_feat) { if (live) vn[e] = __ldg(srcrow + c); }
-                            else if (c == nchunk_feat) vn[e] = xc0;
-                            else if (c == nchunk_feat + 1) vn[e] = xc1;
-                        }
+                for (int sl = w0; sl < w1; ++sl) {
+                    switch (w1 - 1 - sl) {                                      // groups that may still be pending: the younger slices
+                        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+                        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+                        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+                        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+                        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+                        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+                        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+                        case 7: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+                        case 8: asm volatile("cp.async.wait_group 8;" ::: "memory"); break;
+                        case 9: asm volatile("cp.async.wait_group 9;" ::: "memory"); break;
+                        case 10: asm volatile("cp.async.wait_group 10;" ::: "memory"); break;
+                        case 11: asm volatile("cp.async.wait_group 11;" ::: "memory"); break;
+                        case 12: asm volatile("cp.async.wait_group 12;" ::: "memory"); break;
+                        case 13: asm volatile("cp.async.wait_group 13;" ::: "memory"); break;
+                        case 14: asm volatile("cp.async.wait_group 14;" ::: "memory"); break;
+                        default: asm volatile("cp.async.wait_group 15;" ::: "memory"); break;
                     }
-#pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        if (s0 + e2 < S) {                        // uniform
-                            const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                            mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);   // slot free (first lap passes at once)
-                            uint4* dst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
-                            dst[r] = vc[2 * e2];
-                            dst[TILE_M + r] = vc[2 * e2 + 1];
-                            fence_proxy_async();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_full + 8 * slot);
-                            ++it;
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) vc[e] = vn[e];
+                    fence_proxy_async();                                        // copies + stores -> visible to tcgen05.mma
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full + 8 * ((it + sl) % RING));
+                }
                 }
             }
         }
@@ -323,6 +335,8 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 // ---- layer 1: needs TMEM drained by the previous batch's epilogue 3
                 mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
                 tc_fence_after();
+                long long* dbg = (a.dbg && blockIdx.x == 0 && nepi <= 3 * 24) ? a.dbg + (nepi / 3) * 16 : nullptr;
+                if (dbg) dbg[0] = clock64();
                 for (int bi = 0; bi < nb; ++bi)
                     for (int s = 0; s < S; ++s) {
                         const uint32_t slot = it % RING, ph = (it / RING) & 1;
@@ -335,9 +349,11 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                         ++it;
                     }
                 umma_commit(bar_dfull);
+                if (dbg) dbg[1] = clock64();
                 // ---- layer 2: needs H1 written by epilogue 1
                 mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
                 tc_fence_after();
+                if (dbg) dbg[2] = clock64();
                 for (int bi = 0; bi < nb; ++bi)
                     for (int k = 0; k < L.c1 / 16; ++k) {
                         const uint64_t ad = umma_desc(s_h + bi * L.h_bytes + (uint32_t)k * 2 * TILE_M * 16, TILE_M * 16, 128);
@@ -345,9 +361,11 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                         umma_f16(tmem + bi * L.cstride, ad, bd, idesc2, k > 0);
                     }
                 umma_commit(bar_dfull);
+                if (dbg) dbg[3] = clock64();
                 // ---- layer 3, transposed: D3[c3p x 128] = W3 . H2^T
                 mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
                 tc_fence_after();
+                if (dbg) dbg[4] = clock64();
                 for (int bi = 0; bi < nb; ++bi)
                     for (int j = 0; j < L.nb3; ++j)
                         for (int k = 0; k < L.c2 / 16; ++k) {
@@ -356,6 +374,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                             umma_f16(tmem + bi * L.cstride + j * 128, ad, bd, idesc3, k > 0);
                         }
                 umma_commit(bar_dfull);
+                if (dbg) dbg[5] = clock64();
             }
         }
         __syncwarp();                                            // reconverge before the block-wide barrier below
@@ -487,22 +506,28 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             // ---- epilogue 1: D1 -> bias + ReLU -> fp16 -> H
             mbar_wait(bar_dfull, nd & 1); ++nd;
             tc_fence_after();
+            long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0 && nd <= 3 * 24) ? a.dbg + (nd / 3) * 16 + 8 : nullptr;
+            if (dbg) dbg[0] = clock64();
             for (int bi = t_first; bi < nb; bi += t_step) relu_to_h(bi, L.c1, b1);
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_epi);
+            if (dbg) dbg[1] = clock64();
             // ---- epilogue 2 (H1 is dead: MMA 2 has completed when d_full fires)
             mbar_wait(bar_dfull, nd & 1); ++nd;
             tc_fence_after();
+            if (dbg) dbg[2] = clock64();
             for (int bi = t_first; bi < nb; bi += t_step) relu_to_h(bi, L.c2, b2);
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_epi);
+            if (dbg) dbg[3] = clock64();
             // ---- epilogue 3: lane = output channel; max over each neighbourhood's nsample consecutive columns
             mbar_wait(bar_dfull, nd & 1); ++nd;
             tc_fence_after();
+            if (dbg) dbg[4] = clock64();
             if (split_cols) {
                 if (a.nsample <= 64) { for (int j = 0; j < L.nb3; ++j) max_emit64(0, (int)tl, j, half); }
                 else { for (int j = half; j < L.nb3; j += 2) max_emit128(0, (int)tl, j); }
@@ -516,6 +541,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_epi);                  // TMEM drained: the next batch's layer 1 may start
+            if (dbg) dbg[5] = clock64();
             if (staged) {
                 asm volatile("bar.sync 1, %0;" ::"n"(SA_EPI_WARPS * 32) : "memory");     // the 8 epilogue warps only
                 const unsigned gpb = (unsigned)tl * (unsigned)groups_per_tile;            // first centroid of the batch
@@ -543,6 +569,11 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
 }  // namespace g4d
 
 using namespace g4d;
+
+static long long* g_timeline = nullptr;
+// Debug aid: device buffer of >= 25*16 int64 that CTA 0 of the next g4d_sa_mlp_max launches fills with clock64() stamps
+// (per batch: MMA lane [0..5], epilogue warp 0 [8..13]); NULL switches it off.
+G4D_API void g4d_debug_timeline(void* buf) { g_timeline = (long long*)buf; }
 
 G4D_API int g4d_sa_mlp_k0(int c_in) { return (c_in + XYZ_SLOTS + 15) / 16 * 16; }
 
@@ -609,6 +640,7 @@ G4D_API int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int
     a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.feat_pm = (const __half*)feat_pm;
     a.params = (const unsigned char*)params_dev;
     a.out_cm = out_cm; a.out_pm = (__half*)out_pm; a.ctot = out_c_total; a.coff = out_c_off;
+    a.dbg = g_timeline;
 
     cudaError_t e = cudaFuncSetAttribute(sa_mlp_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
     if (e != cudaSuccess) { set_error("sa_mlp_max: shared memory opt-in (%u B): %s", a.L.total_smem, cudaGetErrorString(e)); return (int)e; }

@@ -138,6 +138,9 @@ int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int b, int 
                    const float* new_xyz, const int* idx, const void* feat_pm, float* out_cm, void* out_pm,
                    int out_c_total, int out_c_off, void* stream);
 
+/* debug aid: clock64() timeline of CTA 0 of the following g4d_sa_mlp_max launches (buf: >= 400 int64 on the device; NULL = off) */
+void g4d_debug_timeline(void* buf);
+
 /* Fused feature propagation (no skip features) + optional segmentation head on tcgen05: inverse-distance weights
  * from three_nn's squared distances, 3-tap interpolation, the FP module's 2-layer 1x1-conv MLP (eval BN folded, ReLU)
  * and, when h1 > 0, Conv1d(c2,h1)+BN+ReLU -> Conv1d(h1,h2) -- PointnetFPModule.forward (pointnet2_modules.py:131-156)
