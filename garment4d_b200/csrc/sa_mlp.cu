@@ -122,6 +122,12 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
     }
 }
 
+// Shared-memory matrix descriptor split in halves: the high word (SBO = 128 B, version 1) is constant, the low word is
+// (address >> 4) | (LBO >> 4) << 16 and advances by a plain 32-bit add from one MMA to the next (the issuing lane is a
+// single thread: every dependent instruction on its path is latency, measured ~58 cycles per issued MMA before this).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | lo; }
+
 // Wait used by roles that are far off the critical path (producers waiting for a free ring slot): poll, then sleep.
 // A tight try_wait loop in 8 idle warps would take most of the SM's issue slots away from the epilogue warps.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
@@ -328,7 +334,10 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         // =========================== MMA ISSUER (one lane) ==================================================
         if (lane == 0) {
             mbar_wait(bar_w, 0);
-            uint32_t it = 0, nepi = 0;                           // slices consumed; epilogue hand-offs waited for
+            uint32_t slot = 0, ph = 0, nepi = 0;                 // ring position / phase; epilogue hand-offs waited for
+            const uint32_t ring_lo = desc_lo(s_ring, TILE_M * 16), w1_lo = desc_lo(s_w1, L.c1 * 16), w1_step = (uint32_t)(2 * L.c1 * 16) >> 4;
+            const uint32_t w2_lo = desc_lo(s_w2, L.c2 * 16), w2_step = (uint32_t)(2 * L.c2 * 16) >> 4;
+            const uint32_t w3_step = (uint32_t)(2 * L.c3p * 16) >> 4, h_step = (uint32_t)(2 * TILE_M * 16) >> 4;
             const uint32_t idesc1 = umma_idesc(TILE_M, L.c1), idesc2 = umma_idesc(TILE_M, L.c2), idesc3 = umma_idesc(128, TILE_M);
             for (long long tl = (long long)blockIdx.x * L.tb; tl < a.ntiles; tl += (long long)gridDim.x * L.tb) {
                 const int nb = (int)((a.ntiles - tl) < L.tb ? (a.ntiles - tl) : L.tb);      // tiles in this batch
@@ -337,29 +346,30 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 tc_fence_after();
                 long long* dbg = (a.dbg && blockIdx.x == 0 && nepi <= 3 * 24) ? a.dbg + (nepi / 3) * 16 : nullptr;
                 if (dbg) dbg[0] = clock64();
-                for (int bi = 0; bi < nb; ++bi)
+                for (int bi = 0; bi < nb; ++bi) {
+                    uint32_t blo = w1_lo;
                     for (int s = 0; s < S; ++s) {
-                        const uint32_t slot = it % RING, ph = (it / RING) & 1;
                         mbar_wait(bar_full + 8 * slot, ph);
                         tc_fence_after();
-                        const uint64_t ad = umma_desc(s_ring + slot * SLICE_BYTES, TILE_M * 16, 128);
-                        const uint64_t bd = umma_desc(s_w1 + (uint32_t)s * 2 * L.c1 * 16, L.c1 * 16, 128);
-                        umma_f16(tmem + bi * L.cstride, ad, bd, idesc1, s > 0);
+                        umma_f16(tmem + bi * L.cstride, desc64(ring_lo + slot * (SLICE_BYTES >> 4)), desc64(blo), idesc1, s > 0);
                         umma_commit(bar_empty + 8 * slot);        // slot reusable once this (and earlier) MMAs retire
-                        ++it;
+                        blo += w1_step;
+                        if (++slot == (uint32_t)RING) { slot = 0; ph ^= 1; }
                     }
+                }
                 umma_commit(bar_dfull);
                 if (dbg) dbg[1] = clock64();
                 // ---- layer 2: needs H1 written by epilogue 1
                 mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
                 tc_fence_after();
                 if (dbg) dbg[2] = clock64();
-                for (int bi = 0; bi < nb; ++bi)
+                for (int bi = 0; bi < nb; ++bi) {
+                    uint32_t alo = desc_lo(s_h + bi * L.h_bytes, TILE_M * 16), blo = w2_lo;
                     for (int k = 0; k < L.c1 / 16; ++k) {
-                        const uint64_t ad = umma_desc(s_h + bi * L.h_bytes + (uint32_t)k * 2 * TILE_M * 16, TILE_M * 16, 128);
-                        const uint64_t bd = umma_desc(s_w2 + (uint32_t)k * 2 * L.c2 * 16, L.c2 * 16, 128);
-                        umma_f16(tmem + bi * L.cstride, ad, bd, idesc2, k > 0);
+                        umma_f16(tmem + bi * L.cstride, desc64(alo), desc64(blo), idesc2, k > 0);
+                        alo += h_step; blo += w2_step;
                     }
+                }
                 umma_commit(bar_dfull);
                 if (dbg) dbg[3] = clock64();
                 // ---- layer 3, transposed: D3[c3p x 128] = W3 . H2^T
@@ -367,12 +377,13 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 tc_fence_after();
                 if (dbg) dbg[4] = clock64();
                 for (int bi = 0; bi < nb; ++bi)
-                    for (int j = 0; j < L.nb3; ++j)
+                    for (int j = 0; j < L.nb3; ++j) {
+                        uint32_t alo = desc_lo(s_w3 + (uint32_t)j * 128 * 16, L.c3p * 16), blo = desc_lo(s_h + bi * L.h_bytes, TILE_M * 16);
                         for (int k = 0; k < L.c2 / 16; ++k) {
-                            const uint64_t ad = umma_desc(s_w3 + (uint32_t)k * 2 * L.c3p * 16 + (uint32_t)j * 128 * 16, L.c3p * 16, 128);
-                            const uint64_t bd = umma_desc(s_h + bi * L.h_bytes + (uint32_t)k * 2 * TILE_M * 16, TILE_M * 16, 128);
-                            umma_f16(tmem + bi * L.cstride + j * 128, ad, bd, idesc3, k > 0);
+                            umma_f16(tmem + bi * L.cstride + j * 128, desc64(alo), desc64(blo), idesc3, k > 0);
+                            alo += w3_step; blo += h_step;
                         }
+                    }
                 umma_commit(bar_dfull);
                 if (dbg) dbg[5] = clock64();
             }
