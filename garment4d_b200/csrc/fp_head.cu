@@ -19,7 +19,7 @@
 namespace g4d {
 
 constexpr int FP_TILE = 128;
-constexpr int FP_THREADS = 128;
+constexpr int FP_THREADS = 256;     // warps 0-3: rows / TMEM lanes (weights, epilogues); all 8 warps gather
 
 struct FpLayout {
     int c_in, c1, c2, h1, h2, h2p;      // h2p = 16 when a head is present (classes padded), else 0
@@ -144,12 +144,12 @@ fp_interp_mlp_kernel(const FpArgs a) {
     mbar_wait(bar_w, 0);
 
     const int nchunk = L.c_in >> 3;
-    const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t phase = 0;
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const long long R = (long long)tile * FP_TILE + tid;
-        const bool live = R < a.total_rows;
+        const long long R = (long long)tile * FP_TILE + (tid & (FP_TILE - 1));
+        const bool live = R < a.total_rows && tid < FP_TILE;
         const unsigned cloud = live ? (unsigned)((unsigned long long)R / (unsigned)a.n) : 0u;   // total_rows < 2^32 * n: one 64/32 division
         const int pt = live ? (int)(R - (long long)cloud * a.n) : 0;
         // ---- interpolation weights, exactly the reference's torch arithmetic (pointnet2_modules.py:141-143) ----
@@ -167,41 +167,58 @@ fp_interp_mlp_kernel(const FpArgs a) {
                 const uint32_t base = cloud * (uint32_t)a.m;
                 p0 = base + (uint32_t)__ldg(id); p1 = base + (uint32_t)__ldg(id + 1); p2 = base + (uint32_t)__ldg(id + 2);
             }
-            rowpt[tid] = p0; rowpt[FP_TILE + tid] = p1; rowpt[2 * FP_TILE + tid] = p2;
-            roww[tid] = w0; roww[FP_TILE + tid] = w1; roww[2 * FP_TILE + tid] = w2;
+            if (tid < FP_TILE) {
+                rowpt[tid] = p0; rowpt[FP_TILE + tid] = p1; rowpt[2 * FP_TILE + tid] = p2;
+                roww[tid] = w0; roww[FP_TILE + tid] = w1; roww[2 * FP_TILE + tid] = w2;
+            }
         }
-        __syncwarp();
-        // ---- gather + interpolate: warp w owns rows 32w..32w+31; 8 rows x 4 chunks (16 B) per step ----
+        __syncthreads();
+        // ---- gather + interpolate (all 8 warps) ----
         {
             const int rl = lane & 7, cl = lane >> 3;
             uint4* dst = reinterpret_cast<uint4*>(act);
-            for (int rg = 0; rg < 4; ++rg) {
-                const int row = warp * 32 + rg * 8 + rl;
-                const uint32_t q0 = rowpt[row], q1 = rowpt[FP_TILE + row], q2 = rowpt[2 * FP_TILE + row];
-                const float w0 = roww[row], w1 = roww[FP_TILE + row], w2 = roww[2 * FP_TILE + row];
-                const uint4* s0 = reinterpret_cast<const uint4*>(a.known_pm + (size_t)q0 * L.c_in);
-                const uint4* s1 = reinterpret_cast<const uint4*>(a.known_pm + (size_t)q1 * L.c_in);
-                const uint4* s2 = reinterpret_cast<const uint4*>(a.known_pm + (size_t)q2 * L.c_in);
-                // 4 chunks per lane at a time: all 12 loads (3 taps x 4 chunks) are issued before the first use
-                for (int cb = cl; cb < nchunk; cb += 16) {
-                    uint4 l0[4], l1[4], l2[4];
+            // warp w (of 8) owns rows 16w..16w+15 = 2 groups of 8 rows; 4 chunks per lane per group; the 24 loads of both
+            // groups (3 taps x 4 chunks x 2) are issued before the first use: the gather is pure L2/HBM latency
+            uint32_t q[2][3];
+            float wt[2][3];
+            const uint4* sp[2][3];
+#pragma unroll
+            for (int rg = 0; rg < 2; ++rg) {
+                const int row = warp * 16 + rg * 8 + rl;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    q[rg][k] = rowpt[k * FP_TILE + row];
+                    wt[rg][k] = roww[k * FP_TILE + row];
+                    sp[rg][k] = reinterpret_cast<const uint4*>(a.known_pm + (size_t)q[rg][k] * L.c_in);
+                }
+            }
+            for (int cb = cl; cb < nchunk; cb += 16) {
+                uint4 ld[2][3][4];
+#pragma unroll
+                for (int rg = 0; rg < 2; ++rg)
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int c = cb + 4 * u;
-                        l0[u] = l1[u] = l2[u] = make_uint4(0, 0, 0, 0);
-                        if (c < nchunk && q0 != 0xFFFFFFFFu) { l0[u] = __ldg(s0 + c); l1[u] = __ldg(s1 + c); l2[u] = __ldg(s2 + c); }
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            ld[rg][k][u] = make_uint4(0, 0, 0, 0);
+                            if (c < nchunk && q[rg][0] != 0xFFFFFFFFu) ld[rg][k][u] = __ldg(sp[rg][k] + c);
+                        }
                     }
+#pragma unroll
+                for (int rg = 0; rg < 2; ++rg) {
+                    const int row = warp * 16 + rg * 8 + rl;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int c = cb + 4 * u;
                         if (c < nchunk) {
                             float f0[8], f1[8], f2[8], r[8];
-                            unpack8(l0[u], f0); unpack8(l1[u], f1); unpack8(l2[u], f2);
+                            unpack8(ld[rg][0][u], f0); unpack8(ld[rg][1][u], f1); unpack8(ld[rg][2][u], f2);
 #pragma unroll
                             for (int i = 0; i < 8; ++i)     // interpolate_gpu.cu:96 in the reference build's order
-                                r[i] = __fmaf_rn(w2, f2[i], __fmaf_rn(w0, f0[i], __fmul_rn(w1, f1[i])));
+                                r[i] = __fmaf_rn(wt[rg][2], f2[i], __fmaf_rn(wt[rg][0], f0[i], __fmul_rn(wt[rg][1], f1[i])));
                             uint4 o = make_uint4(0, 0, 0, 0);
-                            if (q0 != 0xFFFFFFFFu)
+                            if (q[rg][0] != 0xFFFFFFFFu)
                                 o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
                             dst[(size_t)c * FP_TILE + row] = o;
                         }
@@ -214,28 +231,38 @@ fp_interp_mlp_kernel(const FpArgs a) {
 
         // ---- layer 1 ----
         if (tid == 0) fp_issue_layer(tmem, s_act, s_w1, L.c_in, L.c1, bar_mma);
-        mbar_wait(bar_mma, phase); phase ^= 1;
-        tc_fence_after();
-        fp_epilogue_relu(lane_taddr, L.c1, b1, act, tid, nullptr, 0);
+        if (warp < 4) {
+            mbar_wait(bar_mma, phase);
+            tc_fence_after();
+            fp_epilogue_relu(lane_taddr, L.c1, b1, act, tid, nullptr, 0);
+        }
+        phase ^= 1;
         tc_fence_before(); fence_proxy_async(); __syncthreads();
         // ---- layer 2 (FP output) ----
         if (tid == 0) fp_issue_layer(tmem, s_act, s_w2, L.c1, L.c2, bar_mma);
-        mbar_wait(bar_mma, phase); phase ^= 1;
-        tc_fence_after();
-        fp_epilogue_relu(lane_taddr, L.c2, b2, act, tid, live ? a.out_feat + ((size_t)cloud * L.c2) * a.n + pt : nullptr, (size_t)a.n);
+        if (warp < 4) {
+            mbar_wait(bar_mma, phase);
+            tc_fence_after();
+            fp_epilogue_relu(lane_taddr, L.c2, b2, act, tid, live ? a.out_feat + ((size_t)cloud * L.c2) * a.n + pt : nullptr, (size_t)a.n);
+        }
+        phase ^= 1;
         tc_fence_before(); fence_proxy_async(); __syncthreads();
         if (L.h1) {
             // ---- head layer 1 ----
             if (tid == 0) fp_issue_layer(tmem, s_act, s_w3, L.c2, L.h1, bar_mma);
-            mbar_wait(bar_mma, phase); phase ^= 1;
-            tc_fence_after();
-            fp_epilogue_relu(lane_taddr, L.h1, b3, act, tid, nullptr, 0);
+            if (warp < 4) {
+                mbar_wait(bar_mma, phase);
+                tc_fence_after();
+                fp_epilogue_relu(lane_taddr, L.h1, b3, act, tid, nullptr, 0);
+            }
+            phase ^= 1;
             tc_fence_before(); fence_proxy_async(); __syncthreads();
             // ---- head layer 2: logits, no activation ----
             if (tid == 0) fp_issue_layer(tmem, s_act, s_w4, L.h1, L.h2p, bar_mma);
-            mbar_wait(bar_mma, phase); phase ^= 1;
-            tc_fence_after();
-            {
+            phase ^= 1;
+            if (warp < 4) {
+                mbar_wait(bar_mma, phase ^ 1);
+                tc_fence_after();
                 float v[16];
                 tmem_ld16(lane_taddr, v);
                 if (live) {
@@ -314,7 +341,7 @@ G4D_API int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int 
     int occ = (int)((227u * 1024u) / (a.L.total_smem + 1024u));
     const int tmem_limit = 512 / (int)a.L.tmem_cols;
     if (occ > tmem_limit) occ = tmem_limit;
-    if (occ > 8) occ = 8;
+    if (occ > 2) occ = 2;          // 128 registers x 256 threads
     if (occ < 1) occ = 1;
     long long grid = (long long)sm_count() * occ;
     if (grid > a.ntiles) grid = a.ntiles;

@@ -167,8 +167,19 @@ struct SaMlpArgs {
     long long* dbg;                  // optional timeline buffer (g4d_debug_timeline), CTA 0 only
 };
 
+// Unstaged channel-major store of one output value (few centroids per batch: nsample >= 64).  Out of line: code size.
+__device__ __noinline__ void store_cm_direct(float* out_cm, unsigned cloud, unsigned p, unsigned m, int ctot, int ch, float o) {
+    while (p >= m) { p -= m; ++cloud; }
+    out_cm[((size_t)cloud * ctot + ch) * m + p] = o;
+}
+
+// One instantiation per (nsample, features present), and single call sites / rolled loops for everything that is not the
+// inner arithmetic: with every variant a run-time branch and every helper inlined at each use the kernel was 107 KB of
+// SASS, three times the 32 KB L1.5 instruction cache, shared by three roles that execute disjoint code.
+template <int NS, bool FEAT>
 __global__ void __launch_bounds__(SA_THREADS)
 sa_mlp_max_kernel(const SaMlpArgs a) {
+    constexpr int LG_NS = NS == 8 ? 3 : NS == 16 ? 4 : NS == 32 ? 5 : NS == 64 ? 6 : 7;
     extern __shared__ __align__(128) unsigned char smem[];
     const SaMlpLayout& L = a.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -214,8 +225,9 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         const int pw = warp - (SA_EPI_WARPS + 1);
         const int grp = pw >> 2;
         const int r = (pw & 3) * 32 + lane;                      // tile row 0..127
-        const int nchunk_feat = a.c_in >> 3;
-        const int lg_tb = a.lg_tb, tbm = L.tb - 1, lg_ns = a.lg_ns;
+        const int nchunk_feat = FEAT ? (a.c_in >> 3) : 0;
+        const int lg_tb = a.lg_tb, tbm = L.tb - 1;
+        constexpr int lg_ns = LG_NS;
         const int bx = (int)blockIdx.x, gx = (int)gridDim.x;
         const unsigned um = (unsigned)a.m;
 #define G4D_TILE_OF(q) ((((bx + ((q) >> lg_tb) * gx)) << lg_tb) + ((q) & tbm))
@@ -268,7 +280,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 xc1 = make_uint4(uhz, 0, 0, 0);
             }
             uint32_t it = it0;
-            if (nchunk_feat == 0) {
+            if (!FEAT) {
                 // xyz-only level: a single slice per tile
                 const uint32_t slot = it % RING, ph = (it / RING) & 1;
                 mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);
@@ -286,10 +298,13 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 const char* srcrow = reinterpret_cast<const char*>(a.feat_pm + (size_t)pt * a.c_in);
                 // (waves of at most min(S, RING) slices: a wave must fit the ring, or waiting for its own slots would deadlock)
                 const int wave = S < RING ? S : RING;
+                uint32_t slot = it % RING, ph = (it / RING) & 1;               // one division per tile; then walked
+#pragma unroll 1
                 for (int w0 = 0; w0 < S; w0 += wave) {
                 const int w1 = (w0 + wave < S) ? w0 + wave : S;
+                const uint32_t slot_w = slot;
+#pragma unroll 1
                 for (int sl = w0; sl < w1; ++sl) {
-                    const uint32_t slot = (it + sl) % RING, ph = ((it + sl) / RING) & 1;
                     mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);           // slot free (first lap passes at once)
                     const uint32_t sdst = s_ring + slot * SLICE_BYTES + (uint32_t)r * 16;
                     uint4* gdst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
@@ -302,7 +317,10 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                         else gdst[h * TILE_M + r] = (c == nchunk_feat) ? xc0 : ((c == nchunk_feat + 1) ? xc1 : make_uint4(0, 0, 0, 0));
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (++slot == (uint32_t)RING) { slot = 0; ph ^= 1; }
                 }
+                uint32_t slot_a = slot_w;
+#pragma unroll 1
                 for (int sl = w0; sl < w1; ++sl) {
                     switch (w1 - 1 - sl) {                                      // groups that may still be pending: the younger slices
                         case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
@@ -324,7 +342,8 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                     }
                     fence_proxy_async();                                        // copies + stores -> visible to tcgen05.mma
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full + 8 * ((it + sl) % RING));
+                    if (lane == 0) mbar_arrive(bar_full + 8 * slot_a);
+                    if (++slot_a == (uint32_t)RING) slot_a = 0;
                 }
                 }
             }
@@ -395,7 +414,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         const int quad = warp & 3, half = warp >> 2;
         const int row = quad * 32 + lane;                         // tile row (layers 1-2) / channel within block (layer 3)
         const uint32_t lane_taddr = tmem + ((uint32_t)(quad * 32) << 16);
-        const int groups_per_tile = TILE_M / a.nsample;
+        constexpr int groups_per_tile = TILE_M / NS;
         uint32_t nd = 0;                                          // d_full hand-offs waited for
         // Work split between the two warps of a quadrant: with tb >= 2 tiles per batch each takes alternate tiles (all
         // columns); with a single tile per batch they split its columns.
@@ -443,14 +462,10 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         int e_bi = 0;
         auto emit = [&](int ch, int g, float mx, float bias) {
             const unsigned gp = e_gp0 + (unsigned)g;
-            if (ch < L.c3 && (gp << a.lg_ns) < (unsigned)a.total_rows) {
+            if (ch < L.c3 && (gp << LG_NS) < (unsigned)a.total_rows) {
                 const float o = fmaxf(mx + bias, 0.f);
                 if (staged) stage[ch * (GS + 1) + e_bi * groups_per_tile + g] = o;
-                else {
-                    unsigned cloud = e_cloud0, p = e_p0 + (unsigned)g;
-                    while (p >= (unsigned)a.m) { p -= (unsigned)a.m; ++cloud; }
-                    a.out_cm[((size_t)cloud * a.ctot + a.coff + ch) * a.m + p] = o;
-                }
+                else store_cm_direct(a.out_cm, e_cloud0, e_p0 + (unsigned)g, (unsigned)a.m, a.ctot, a.coff + ch, o);
                 if (a.out_pm) a.out_pm[(size_t)gp * a.ctot + a.coff + ch] = __float2half_rn(fminf(o, 65504.f));
             }
         };
@@ -466,8 +481,8 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             float v[64];
             tmem_ld_cols<4>(lane_taddr + bi * L.cstride + j * 128 + 64 * colhalf, v);
             set_tile(tile); e_bi = bi;
-            const int gp0 = (64 * colhalf) >> a.lg_ns;
-            if (a.nsample == 8) {
+            const int gp0 = (64 * colhalf) >> LG_NS;
+            if constexpr (NS == 8) {
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     float mx = v[8 * g];
@@ -475,7 +490,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                     for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[8 * g + i]);
                     emit(ch, gp0 + g, mx, bias);
                 }
-            } else if (a.nsample == 16) {
+            } else if constexpr (NS == 16) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     float mx = v[16 * g];
@@ -483,7 +498,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                     for (int i = 1; i < 16; ++i) mx = fmaxf(mx, v[16 * g + i]);
                     emit(ch, gp0 + g, mx, bias);
                 }
-            } else if (a.nsample == 32) {
+            } else if constexpr (NS == 32) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     float mx = v[32 * g];
@@ -514,40 +529,43 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         const int t_first = split_cols ? 0 : half, t_step = split_cols ? 1 : 2;
         for (long long tl = (long long)blockIdx.x * L.tb; tl < a.ntiles; tl += (long long)gridDim.x * L.tb) {
             const int nb = (int)((a.ntiles - tl) < L.tb ? (a.ntiles - tl) : L.tb);
-            // ---- epilogue 1: D1 -> bias + ReLU -> fp16 -> H
-            mbar_wait(bar_dfull, nd & 1); ++nd;
-            tc_fence_after();
-            long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0 && nd <= 3 * 24) ? a.dbg + (nd / 3) * 16 + 8 : nullptr;
-            if (dbg) dbg[0] = clock64();
-            for (int bi = t_first; bi < nb; bi += t_step) relu_to_h(bi, L.c1, b1);
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_epi);
-            if (dbg) dbg[1] = clock64();
-            // ---- epilogue 2 (H1 is dead: MMA 2 has completed when d_full fires)
-            mbar_wait(bar_dfull, nd & 1); ++nd;
-            tc_fence_after();
-            if (dbg) dbg[2] = clock64();
-            for (int bi = t_first; bi < nb; bi += t_step) relu_to_h(bi, L.c2, b2);
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_epi);
-            if (dbg) dbg[3] = clock64();
+            // ---- epilogues 1 and 2: D -> bias + ReLU -> fp16 -> H (H1 is dead when d_full fires for layer 2: MMA 2 has completed).
+            // One body for both layers (code size).
+            long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0 && nd < 3 * 24) ? a.dbg + (nd / 3) * 16 + 8 : nullptr;
+#pragma unroll 1
+            for (int layer = 0; layer < 2; ++layer) {
+                mbar_wait(bar_dfull, nd & 1); ++nd;
+                tc_fence_after();
+                if (dbg) dbg[2 * layer] = clock64();
+                const int ncols = layer ? L.c2 : L.c1;
+                const float* bias = layer ? b2 : b1;
+#pragma unroll 1
+                for (int bi = t_first; bi < nb; bi += t_step) relu_to_h(bi, ncols, bias);
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_epi);
+                if (dbg) dbg[2 * layer + 1] = clock64();
+            }
             // ---- epilogue 3: lane = output channel; max over each neighbourhood's nsample consecutive columns
             mbar_wait(bar_dfull, nd & 1); ++nd;
             tc_fence_after();
             if (dbg) dbg[4] = clock64();
-            if (split_cols) {
-                if (a.nsample <= 64) { for (int j = 0; j < L.nb3; ++j) max_emit64(0, (int)tl, j, half); }
-                else { for (int j = half; j < L.nb3; j += 2) max_emit128(0, (int)tl, j); }
-            } else {
+            if constexpr (NS <= 64) {
+                // work items (tile, channel block, column half); with one tile per batch the two warps of a quadrant split the halves
+                const int h_first = split_cols ? half : 0, h_step = split_cols ? 2 : 1;
+#pragma unroll 1
                 for (int bi = t_first; bi < nb; bi += t_step)
-                    for (int j = 0; j < L.nb3; ++j) {
-                        if (a.nsample <= 64) { max_emit64(bi, (int)tl + bi, j, 0); max_emit64(bi, (int)tl + bi, j, 1); }
-                        else max_emit128(bi, (int)tl + bi, j);
-                    }
+#pragma unroll 1
+                    for (int j = 0; j < L.nb3; ++j)
+#pragma unroll 1
+                        for (int ch2 = h_first; ch2 < 2; ch2 += h_step) max_emit64(bi, (int)tl + bi, j, ch2);
+            } else {
+                const int j_first = split_cols ? half : 0, j_step = split_cols ? 2 : 1;
+#pragma unroll 1
+                for (int bi = t_first; bi < nb; bi += t_step)
+#pragma unroll 1
+                    for (int j = j_first; j < L.nb3; j += j_step) max_emit128(bi, (int)tl + bi, j);
             }
             tc_fence_before();
             __syncwarp();
@@ -561,7 +579,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 const int et = warp * 32 + lane;                  // 0..255
                 for (int i = et; i < L.c3 * G; i += SA_EPI_WARPS * 32) {
                     const int ch = i / G, g = i - ch * G;
-                    if (((gpb + (unsigned)g) << a.lg_ns) < (unsigned)a.total_rows) {
+                    if (((gpb + (unsigned)g) << LG_NS) < (unsigned)a.total_rows) {
                         unsigned cloud = cloudb, pp = pb + (unsigned)g;
                         while (pp >= (unsigned)a.m) { pp -= (unsigned)a.m; ++cloud; }
                         a.out_cm[((size_t)cloud * a.ctot + a.coff + ch) * a.m + pp] = stage[ch * (GS + 1) + g];
@@ -653,9 +671,19 @@ G4D_API int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int
     a.out_cm = out_cm; a.out_pm = (__half*)out_pm; a.ctot = out_c_total; a.coff = out_c_off;
     a.dbg = g_timeline;
 
-    cudaError_t e = cudaFuncSetAttribute(sa_mlp_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
+    typedef void (*kern_t)(const SaMlpArgs);
+    kern_t kern = nullptr;
+    const bool feat = d->c_in > 0;
+    switch (d->nsample) {
+        case 8: kern = feat ? sa_mlp_max_kernel<8, true> : sa_mlp_max_kernel<8, false>; break;
+        case 16: kern = feat ? sa_mlp_max_kernel<16, true> : sa_mlp_max_kernel<16, false>; break;
+        case 32: kern = feat ? sa_mlp_max_kernel<32, true> : sa_mlp_max_kernel<32, false>; break;
+        case 64: kern = feat ? sa_mlp_max_kernel<64, true> : sa_mlp_max_kernel<64, false>; break;
+        default: kern = feat ? sa_mlp_max_kernel<128, true> : sa_mlp_max_kernel<128, false>; break;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
     if (e != cudaSuccess) { set_error("sa_mlp_max: shared memory opt-in (%u B): %s", a.L.total_smem, cudaGetErrorString(e)); return (int)e; }
-    cudaFuncSetAttribute(sa_mlp_max_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     // resident CTAs per SM: shared memory (227 KB usable, 1 KB reserved per CTA), TMEM columns (512 per SM), threads
     int occ = (int)((227u * 1024u) / (a.L.total_smem + 1024u));
     const int tmem_limit = 512 / (int)a.L.tmem_cols;
@@ -665,6 +693,6 @@ G4D_API int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int
     long long grid = (long long)sm_count() * occ;
     const long long nbatches = (a.ntiles + a.L.tb - 1) / a.L.tb;
     if (grid > nbatches) grid = nbatches;
-    sa_mlp_max_kernel<<<(unsigned)grid, SA_THREADS, a.L.total_smem, (cudaStream_t)stream>>>(a);
+    kern<<<(unsigned)grid, SA_THREADS, a.L.total_smem, (cudaStream_t)stream>>>(a);
     return finish_launch("g4d sa_mlp_max");
 }
