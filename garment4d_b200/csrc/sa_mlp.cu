@@ -36,13 +36,16 @@ namespace g4d {
 
 constexpr int TILE_M = 128;
 constexpr int XYZ_SLOTS = 9;                 // [hi(3) | lo(3) | hi(3)] against weights [wh | wh | wl]
-constexpr int SA_EPI_WARPS = 8, SA_PROD_WARPS = 8;   // 2 epilogue warps per TMEM lane quadrant (they split the columns)
-constexpr int SA_THREADS = (SA_EPI_WARPS + 1 + SA_PROD_WARPS) * 32;     // 544
+// Warp groups per role, WG (template parameter of the kernel): WG x 4 epilogue warps + 1 MMA warp + WG x 4 producer warps.
+//   WG = 2 (544 threads, 1 CTA per SM): two epilogue warps per TMEM lane quadrant, two producer groups on alternate tiles;
+//   WG = 1 (288 threads, 2 CTAs per SM, half the TMEM each): two independent producer -> MMA -> epilogue chains per SM.  The
+//          chain is latency-bound (every layer is MMA issue -> commit -> epilogue -> arrive), so the second CTA fills the bubbles.
+__host__ __device__ constexpr int sa_threads(int wg) { return (8 * wg + 1) * 32; }
 constexpr int SLICE_BYTES = TILE_M * 16 * 2;  // one K-slice: 128 rows x 16 channels fp16 = 4 KB
 constexpr int MAX_RING = 16;
 
 struct SaMlpLayout {
-    int k0, c1, c2, c3, c3p, nb3, nslices, ring, tb;        // tb = tiles per batch (hand-off latency amortised over tb tiles)
+    int k0, c1, c2, c3, c3p, nb3, nslices, ring, tb, wg;        // tb = tiles per batch (hand-off latency amortised over tb tiles)
     uint32_t h_bytes, cstride;                              // per-tile H buffer bytes, per-tile TMEM column stride
     uint32_t off_w1, off_w2, off_w3, off_b1, off_b2, off_b3, blob_bytes;   // inside the parameter blob == smem image
     uint32_t off_h, off_ring, off_bar, total_smem;
@@ -77,26 +80,40 @@ static bool make_layout(const g4d_sa_mlp_desc* d, SaMlpLayout* L, const char** w
     L->h_bytes = (uint32_t)TILE_M * hk * 2;
     L->cstride = (uint32_t)(128 * L->nb3) > (uint32_t)hk ? 128 * L->nb3 : hk;
     L->off_h = round_up(o, 128);
-    const uint32_t budget = 227u * 1024u - 512u;
-    // tiles per batch: as many as TMEM (512 columns) and shared memory allow, up to 4 (env G4D_SA_TB overrides)
-    int tb = 512 / (int)L->cstride;
-    if (tb > 4) tb = 4;
-    if (tb == 3) tb = 2;
-    if (const char* e = getenv("G4D_SA_TB")) { const int v = atoi(e); if (v >= 1 && v <= tb) tb = v; }
-    while (tb > 1 && L->off_h + (uint32_t)tb * L->h_bytes + 4u * SLICE_BYTES > budget) tb >>= 1;
-    L->tb = tb;
-    L->off_ring = L->off_h + (uint32_t)tb * L->h_bytes;
-    // ring depth: two tiles' worth of slices when they fit (producers run ahead), at least 2, at most 16
-    int ring = 2 * L->nslices;
-    if (ring < 4) ring = 4;
-    if (ring > MAX_RING) ring = MAX_RING;
-    while (ring > 2 && L->off_ring + (uint32_t)ring * SLICE_BYTES > budget) --ring;
-    L->ring = ring;
-    L->off_bar = L->off_ring + (uint32_t)ring * SLICE_BYTES;
-    L->total_smem = L->off_bar + 8 * (2 * MAX_RING + 4) + 16;
-    uint32_t p2 = 32;
-    while (p2 < (uint32_t)tb * L->cstride) p2 <<= 1;
-    L->tmem_cols = p2;
+    // Plan for `occ` resident CTAs per SM (occ = 2 <=> WG = 1): shared memory and the 512 TMEM columns are split evenly.
+    auto plan = [&](int occ) -> bool {
+        const uint32_t budget = (227u * 1024u) / occ - 1024u - 512u;             // 1 KB per CTA is reserved by the driver
+        if (L->off_h + L->h_bytes + 2u * SLICE_BYTES > budget) return false;
+        // tiles per batch: as many as TMEM and shared memory allow, up to 4 per SM (env G4D_SA_TB overrides)
+        int tb = (512 / occ) / (int)L->cstride;
+        if (tb < 1) return false;
+        if (tb > 4 / occ) tb = 4 / occ;
+        if (tb == 3) tb = 2;
+        if (const char* e = getenv("G4D_SA_TB")) { const int v = atoi(e); if (v >= 1 && v <= tb) tb = v; }
+        while (tb > 1 && L->off_h + (uint32_t)tb * L->h_bytes + 4u * SLICE_BYTES > budget) tb >>= 1;
+        L->tb = tb;
+        L->off_ring = L->off_h + (uint32_t)tb * L->h_bytes;
+        // ring depth: two tiles' worth of slices when they fit (producers run ahead), at least 2, at most 16
+        int ring = 2 * L->nslices;
+        if (ring < 4) ring = 4;
+        if (ring > MAX_RING) ring = MAX_RING;
+        while (ring > 2 && L->off_ring + (uint32_t)ring * SLICE_BYTES > budget) --ring;
+        if (occ > 1 && ring < 8 && ring < L->nslices) return false;              // too shallow to hide the gather: use the big CTA
+        L->ring = ring;
+        L->off_bar = L->off_ring + (uint32_t)ring * SLICE_BYTES;
+        L->total_smem = L->off_bar + 8 * (2 * MAX_RING + 4) + 16;
+        uint32_t p2 = 32;
+        while (p2 < (uint32_t)tb * L->cstride) p2 <<= 1;
+        L->tmem_cols = p2;
+        L->wg = occ == 1 ? 2 : 1;
+        return L->total_smem <= budget + 512u;
+    };
+    int want_wg = 0;
+    if (const char* e = getenv("G4D_SA_WG")) want_wg = atoi(e);
+    bool ok = false;
+    if (want_wg != 2) ok = plan(2);
+    if (!ok) ok = plan(1);
+    if (!ok) { *why = msgs[5]; return false; }
     if (L->total_smem > 227 * 1024) { *why = msgs[5]; return false; }
     return true;
 }
@@ -144,6 +161,19 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     }
 }
 
+// Spinning wait (no suspend-time hint) for the single MMA-issuing lane: it is the critical path of every hand-off.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -176,9 +206,10 @@ __device__ __noinline__ void store_cm_direct(float* out_cm, unsigned cloud, unsi
 // One instantiation per (nsample, features present), and single call sites / rolled loops for everything that is not the
 // inner arithmetic: with every variant a run-time branch and every helper inlined at each use the kernel was 107 KB of
 // SASS, three times the 32 KB L1.5 instruction cache, shared by three roles that execute disjoint code.
-template <int NS, bool FEAT>
-__global__ void __launch_bounds__(SA_THREADS)
+template <int NS, bool FEAT, int WG>
+__global__ void __launch_bounds__(sa_threads(WG), 3 - WG)
 sa_mlp_max_kernel(const SaMlpArgs a) {
+    constexpr int SA_EPI_WARPS = 4 * WG, SA_THREADS = sa_threads(WG);
     constexpr int LG_NS = NS == 8 ? 3 : NS == 16 ? 4 : NS == 32 ? 5 : NS == 64 ? 6 : 7;
     extern __shared__ __align__(128) unsigned char smem[];
     const SaMlpLayout& L = a.L;
@@ -223,7 +254,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         // nsample / tiles-per-batch are powers of two; the code is written flat on purpose (no helper objects: the
         // per-tile instruction count of this role bounds the small layers).
         const int pw = warp - (SA_EPI_WARPS + 1);
-        const int grp = pw >> 2;
+        const int grp = pw >> 2;                                 // 0 .. WG-1
         const int r = (pw & 3) * 32 + lane;                      // tile row 0..127
         const int nchunk_feat = FEAT ? (a.c_in >> 3) : 0;
         const int lg_tb = a.lg_tb, tbm = L.tb - 1;
@@ -232,7 +263,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         const unsigned um = (unsigned)a.m;
 #define G4D_TILE_OF(q) ((((bx + ((q) >> lg_tb) * gx)) << lg_tb) + ((q) & tbm))
         int seq = grp;
-        int t_cur = G4D_TILE_OF(seq), t_nxt = G4D_TILE_OF(seq + 2);
+        int t_cur = G4D_TILE_OF(seq), t_nxt = G4D_TILE_OF(seq + WG);
         // pipeline registers: source index of the next two tiles, geometry + point id of the next tile
         int src_n = 0, src_nn = 0;
         float npx = 0.f, npy = 0.f, npz = 0.f, nqx = 0.f, nqy = 0.f, nqz = 0.f;
@@ -254,9 +285,9 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             const unsigned pt = npt;
             const uint32_t it0 = (uint32_t)seq * (uint32_t)S;      // global slice counter of this tile's first slice
             // ---- advance the pipeline: issue the loads of the following tiles before touching this one
-            seq += 2;
+            seq += WG;
             t_cur = t_nxt;
-            t_nxt = G4D_TILE_OF(seq + 2);
+            t_nxt = G4D_TILE_OF(seq + WG);
             src_n = src_nn;
             src_nn = 0;
             if (t_nxt < a.ntiles && t_nxt * TILE_M + r < a.total_rows) src_nn = __ldg(a.idx + t_nxt * TILE_M + r);
@@ -361,14 +392,15 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             for (long long tl = (long long)blockIdx.x * L.tb; tl < a.ntiles; tl += (long long)gridDim.x * L.tb) {
                 const int nb = (int)((a.ntiles - tl) < L.tb ? (a.ntiles - tl) : L.tb);      // tiles in this batch
                 // ---- layer 1: needs TMEM drained by the previous batch's epilogue 3
-                mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
+                mbar_wait_spin(bar_epi, (nepi + 1) & 1); ++nepi;
                 tc_fence_after();
                 long long* dbg = (a.dbg && blockIdx.x == 0 && nepi <= 3 * 24) ? a.dbg + (nepi / 3) * 16 : nullptr;
                 if (dbg) dbg[0] = clock64();
                 for (int bi = 0; bi < nb; ++bi) {
                     uint32_t blo = w1_lo;
                     for (int s = 0; s < S; ++s) {
-                        mbar_wait(bar_full + 8 * slot, ph);
+                        if constexpr (FEAT) mbar_wait(bar_full + 8 * slot, ph);   // gathers in flight: leave the issue slots to the producers
+                        else mbar_wait_spin(bar_full + 8 * slot, ph);
                         tc_fence_after();
                         umma_f16(tmem + bi * L.cstride, desc64(ring_lo + slot * (SLICE_BYTES >> 4)), desc64(blo), idesc1, s > 0);
                         umma_commit(bar_empty + 8 * slot);        // slot reusable once this (and earlier) MMAs retire
@@ -379,7 +411,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 umma_commit(bar_dfull);
                 if (dbg) dbg[1] = clock64();
                 // ---- layer 2: needs H1 written by epilogue 1
-                mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
+                mbar_wait_spin(bar_epi, (nepi + 1) & 1); ++nepi;
                 tc_fence_after();
                 if (dbg) dbg[2] = clock64();
                 for (int bi = 0; bi < nb; ++bi) {
@@ -392,7 +424,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 umma_commit(bar_dfull);
                 if (dbg) dbg[3] = clock64();
                 // ---- layer 3, transposed: D3[c3p x 128] = W3 . H2^T
-                mbar_wait(bar_epi, (nepi + 1) & 1); ++nepi;
+                mbar_wait_spin(bar_epi, (nepi + 1) & 1); ++nepi;
                 tc_fence_after();
                 if (dbg) dbg[4] = clock64();
                 for (int bi = 0; bi < nb; ++bi)
@@ -418,7 +450,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         uint32_t nd = 0;                                          // d_full hand-offs waited for
         // Work split between the two warps of a quadrant: with tb >= 2 tiles per batch each takes alternate tiles (all
         // columns); with a single tile per batch they split its columns.
-        const bool split_cols = L.tb == 1;
+        const bool split_cols = WG == 2 && L.tb == 1;
         auto relu_to_h = [&](int bi, int ncols, const float* bias) {
             const int units = ncols / 16;
             const int u0 = (!split_cols || half == 0) ? 0 : (units + 1) / 2;
@@ -526,7 +558,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             set_tile(tile); e_bi = bi;
             emit(ch, 0, mx, b3[ch]);
         };
-        const int t_first = split_cols ? 0 : half, t_step = split_cols ? 1 : 2;
+        const int t_first = split_cols ? 0 : half, t_step = split_cols ? 1 : WG;
         for (long long tl = (long long)blockIdx.x * L.tb; tl < a.ntiles; tl += (long long)gridDim.x * L.tb) {
             const int nb = (int)((a.ntiles - tl) < L.tb ? (a.ntiles - tl) : L.tb);
             // ---- epilogues 1 and 2: D -> bias + ReLU -> fp16 -> H (H1 is dead when d_full fires for layer 2: MMA 2 has completed).
@@ -674,25 +706,24 @@ G4D_API int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int
     typedef void (*kern_t)(const SaMlpArgs);
     kern_t kern = nullptr;
     const bool feat = d->c_in > 0;
+#define G4D_SA_PICK(NS_) \
+    kern = a.L.wg == 1 ? (feat ? sa_mlp_max_kernel<NS_, true, 1> : sa_mlp_max_kernel<NS_, false, 1>) \
+                       : (feat ? sa_mlp_max_kernel<NS_, true, 2> : sa_mlp_max_kernel<NS_, false, 2>)
     switch (d->nsample) {
-        case 8: kern = feat ? sa_mlp_max_kernel<8, true> : sa_mlp_max_kernel<8, false>; break;
-        case 16: kern = feat ? sa_mlp_max_kernel<16, true> : sa_mlp_max_kernel<16, false>; break;
-        case 32: kern = feat ? sa_mlp_max_kernel<32, true> : sa_mlp_max_kernel<32, false>; break;
-        case 64: kern = feat ? sa_mlp_max_kernel<64, true> : sa_mlp_max_kernel<64, false>; break;
-        default: kern = feat ? sa_mlp_max_kernel<128, true> : sa_mlp_max_kernel<128, false>; break;
+        case 8: G4D_SA_PICK(8); break;
+        case 16: G4D_SA_PICK(16); break;
+        case 32: G4D_SA_PICK(32); break;
+        case 64: G4D_SA_PICK(64); break;
+        default: G4D_SA_PICK(128); break;
     }
+#undef G4D_SA_PICK
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
     if (e != cudaSuccess) { set_error("sa_mlp_max: shared memory opt-in (%u B): %s", a.L.total_smem, cudaGetErrorString(e)); return (int)e; }
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    // resident CTAs per SM: shared memory (227 KB usable, 1 KB reserved per CTA), TMEM columns (512 per SM), threads
-    int occ = (int)((227u * 1024u) / (a.L.total_smem + 1024u));
-    const int tmem_limit = 512 / (int)a.L.tmem_cols;
-    if (occ > tmem_limit) occ = tmem_limit;
-    if (occ > 2048 / SA_THREADS) occ = 2048 / SA_THREADS;
-    if (occ < 1) occ = 1;
+    const int occ = a.L.wg == 1 ? 2 : 1;                   // resident CTAs per SM the layout was planned for (make_layout)
     long long grid = (long long)sm_count() * occ;
     const long long nbatches = (a.ntiles + a.L.tb - 1) / a.L.tb;
     if (grid > nbatches) grid = nbatches;
-    kern<<<(unsigned)grid, SA_THREADS, a.L.total_smem, (cudaStream_t)stream>>>(a);
+    kern<<<(unsigned)grid, sa_threads(a.L.wg), a.L.total_smem, (cudaStream_t)stream>>>(a);
     return finish_launch("g4d sa_mlp_max");
 }
