@@ -38,8 +38,8 @@ def test_library_is_sm100a_native_and_has_tcgen05():
     from garment4d_b200 import _lib
     out = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3g4d17sa_mlp_max_kernelENS_9SaMlpArgsE", _lib.SO_PATH],
-                          capture_output=True, text=True).stdout
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3g4d17sa_mlp_max_kernelILi32ELb1ELi1EEEvNS_9SaMlpArgsE",
+                           _lib.SO_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass, "grouped-MLP kernel is not on the tcgen05 path"
 
 
