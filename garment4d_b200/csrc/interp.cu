@@ -169,3 +169,95 @@ G4D_API int g4d_bias_relu_inplace(int b, int c, long long n, float* y, const flo
     }
     return finish_launch("g4d bias_relu_inplace");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Front half of PointnetFPModule.forward in one pass (eval route; pointnet2_modules.py:138-152):
+//     dist_recip = 1 / (dist + 1e-8) ; norm = sum(dist_recip) ; weight = dist_recip / norm        (5 torch kernels)
+//     interpolated = three_interpolate(known_feats, idx, weight)                                  (interpolate_gpu.cu:77-97)
+//     new_features = cat([interpolated, unknow_feats], dim=1)                                     (1 torch kernel)
+// One thread per unknown point: the weights are computed once (correctly rounded sqrt / divide in torch's order, so they
+// equal the torch tensors bit for bit), then the thread walks a slab of output channels; the skip channels are a
+// coalesced copy.  Same FMUL/FFMA order as three_interpolate_kernel.
+namespace g4d {
+__global__ void __launch_bounds__(256)
+fp_interp_concat_kernel(int c2, int c1, int m, int n, const float* __restrict__ dist2, const int* __restrict__ idx,
+                        const float* __restrict__ known_feats, const float* __restrict__ skip, float* __restrict__ out) {
+    const size_t bi = blockIdx.z;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= n) return;
+    const int ctot = c2 + c1;
+    int i0 = 0, i1 = 0, i2 = 0;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+    if ((int)blockIdx.y < c2) {                     // this channel slab holds at least one interpolated channel
+        const int* id = idx + (bi * n + pt) * 3;
+        const float* d2 = dist2 + (bi * n + pt) * 3;
+        i0 = __ldg(id); i1 = __ldg(id + 1); i2 = __ldg(id + 2);
+        const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2)), 1e-8f));
+        const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 1)), 1e-8f));
+        const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 2)), 1e-8f));
+        const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        w0 = __fdiv_rn(r0, norm); w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm);
+    }
+    for (int ci = blockIdx.y; ci < ctot; ci += gridDim.y) {
+        float v;
+        if (ci < c2) {
+            const float* p = known_feats + (bi * c2 + ci) * (size_t)m;
+            v = __fmaf_rn(w2, __ldg(p + i2), __fmaf_rn(w0, __ldg(p + i0), __fmul_rn(w1, __ldg(p + i1))));
+        } else {
+            v = __ldg(skip + (bi * c1 + (ci - c2)) * (size_t)n + pt);
+        }
+        out[(bi * ctot + ci) * (size_t)n + pt] = v;
+    }
+}
+
+// y (b,c,n) fp32 channel-major: y = act(y + bias[c]) in place AND the same values as fp16 point-major (b,n,c) -- the gather
+// layout of the fused tcgen05 kernels (replaces a bias/ReLU pass + transpose().to(half).contiguous() = 3 passes).
+// 32 x 32 (channel x point) tiles through shared memory; both the fp32 read-modify-write and the fp16 write are coalesced.
+__global__ void __launch_bounds__(256)
+bias_relu_pm_kernel(int c, int n, int relu, float* __restrict__ y, const float* __restrict__ bias, __half* __restrict__ out_pm) {
+    __shared__ float tile[32][33];
+    const size_t bi = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ch = c0 + ty + 8 * r, pt = p0 + tx;
+        float v = 0.f;
+        if (ch < c && pt < n) {
+            float* q = y + (bi * c + ch) * (size_t)n + pt;
+            v = *q + __ldg(bias + ch);
+            if (relu) v = fmaxf(v, 0.f);
+            *q = v;
+        }
+        tile[ty + 8 * r][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int pt = p0 + ty + 8 * r, ch = c0 + tx;
+        if (ch < c && pt < n) out_pm[(bi * n + pt) * (size_t)c + ch] = __float2half_rn(fminf(tile[tx][ty + 8 * r], 65504.f));
+    }
+}
+}  // namespace g4d
+
+G4D_API int g4d_fp_interp_concat(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const float* known_feats,
+                                 const float* skip, float* out, void* stream) {
+    if (b < 0 || c2 < 0 || c1 < 0 || n < 0 || m < 0) return bad_arg("fp_interp_concat: negative size");
+    if (b == 0 || n == 0 || c2 + c1 == 0) return 0;
+    if (!out || (c2 > 0 && (!dist2 || !idx || !known_feats || m == 0)) || (c1 > 0 && !skip)) return bad_arg("fp_interp_concat: null pointer");
+    if (b > 65535) return bad_arg("fp_interp_concat: b > 65535");
+    const int ctot = c2 + c1;
+    dim3 grid((n + 255) / 256, ctot < 16 ? ctot : 16, b);
+    fp_interp_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c2, c1, m, n, dist2, idx, known_feats, skip, out);
+    return finish_launch("g4d fp_interp_concat");
+}
+
+G4D_API int g4d_bias_relu_pm(int b, int c, int n, float* y, const float* bias, int relu, void* out_pm, void* stream) {
+    if (b < 0 || c < 0 || n < 0) return bad_arg("bias_relu_pm: negative size");
+    if (b == 0 || c == 0 || n == 0) return 0;
+    if (!y || !bias || !out_pm) return bad_arg("bias_relu_pm: null pointer");
+    if (b > 65535 || (c + 31) / 32 > 65535) return bad_arg("bias_relu_pm: b or c/32 > 65535");
+    dim3 grid((n + 31) / 32, (c + 31) / 32, b);
+    bias_relu_pm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, relu, y, bias, (__half*)out_pm);
+    return finish_launch("g4d bias_relu_pm");
+}

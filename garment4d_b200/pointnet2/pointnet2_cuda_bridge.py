@@ -75,7 +75,10 @@ def fp_interp_mlp(packed, unknown, known, known_feats):
     dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
     idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
     three_nn_raw(unknown, known, dist2, idx)
-    known_pm = known_feats.detach().transpose(1, 2).to(torch.float16).contiguous()
+    known_pm = getattr(known_feats, "_g4d_pm", None)       # emitted by the producing FP level's epilogue (g4d_bias_relu_pm)
+    if (known_pm is None or known_pm.dtype != torch.float16 or tuple(known_pm.shape) != (B, m, known_feats.shape[1])
+            or not known_pm.is_contiguous()):
+        known_pm = known_feats.detach().transpose(1, 2).to(torch.float16).contiguous()
     feat = torch.empty(B, packed.c2, n, dtype=torch.float32, device=unknown.device)
     logits = torch.empty(B, n, packed.h2, dtype=torch.float32, device=unknown.device)
     rc = _lib.lib().g4d_fp_interp_mlp(ctypes.byref(packed.desc), _lib.ptr(packed.params), B, n, m, _lib.ptr(dist2), _lib.ptr(idx),

@@ -204,27 +204,50 @@ class PointnetFPModule(nn.Module):
     def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
                 known_feats: torch.Tensor) -> torch.Tensor:
         """unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n), known_feats (B,C2,m) -> (B, mlp[-1], n)"""
-        if known is not None:
-            dist, idx = pointnet2_utils.three_nn(unknown.contiguous(), known.contiguous())
-            dist_recip = 1.0 / (dist + 1e-8)
-            norm = torch.sum(dist_recip, dim=2, keepdim=True)
-            weight = dist_recip / norm
-            interpolated_feats = pointnet2_utils.three_interpolate(known_feats.contiguous(), idx, weight)
+        folded = self._folded_mlp(known_feats, unknow_feats)
+        L = _lib.lib() if folded is not None else None
+        if (folded is not None and known is not None and known_feats.dtype == torch.float32
+                and (unknow_feats is None or unknow_feats.dtype == torch.float32)):
+            # eval route: three_nn -> ONE kernel for weights + three_interpolate + cat (g4d_fp_interp_concat)
+            unknown, known, known_feats = unknown.contiguous(), known.contiguous(), known_feats.contiguous()
+            B, n, _ = unknown.shape
+            m, c2 = known.shape[1], known_feats.shape[1]
+            c1 = 0 if unknow_feats is None else unknow_feats.shape[1]
+            skip = None if unknow_feats is None else unknow_feats.contiguous()
+            dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
+            idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
+            pointnet2_utils.three_nn_raw(unknown, known, dist2, idx)
+            new_features = torch.empty(B, c2 + c1, n, dtype=torch.float32, device=unknown.device)
+            rc = L.g4d_fp_interp_concat(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(known_feats), _lib.ptr(skip),
+                                        _lib.ptr(new_features), _lib.stream_ptr())
+            _lib.check(rc, "g4d_fp_interp_concat")
         else:
-            interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
-        if unknow_feats is not None:
-            new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
-        else:
-            new_features = interpolated_feats
-        folded = self._folded_mlp(new_features)
+            if known is not None:
+                dist, idx = pointnet2_utils.three_nn(unknown.contiguous(), known.contiguous())
+                dist_recip = 1.0 / (dist + 1e-8)
+                norm = torch.sum(dist_recip, dim=2, keepdim=True)
+                weight = dist_recip / norm
+                interpolated_feats = pointnet2_utils.three_interpolate(known_feats.contiguous(), idx, weight)
+            else:
+                interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+            if unknow_feats is not None:
+                new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
+            else:
+                new_features = interpolated_feats
         if folded is not None:
-            # eval mode, no autograd: BatchNorm folded into the 1x1 convolutions -> conv(+bias) and in-place ReLU per layer
-            # eval mode: library GEMM (1x1 conv, no bias) + ONE in-place bias+ReLU pass of ours per layer
+            # eval mode, no autograd: BatchNorm folded into the 1x1 convolutions -> library GEMM (1x1 conv, no bias) + ONE
+            # in-place bias+ReLU pass of ours per layer; the last layer's pass also emits the fp16 point-major copy that the
+            # next (finer) level's fused kernel gathers from (attached as ``_g4d_pm``, like the SA modules do)
             y = new_features
-            L = _lib.lib()
-            for w, b in folded:
+            for li, (w, b) in enumerate(folded):
                 y = F.conv2d(y.unsqueeze(-1), w).squeeze(-1)
-                if y.shape[0] * y.shape[1] <= 65535 and y.is_contiguous():
+                last = li == len(folded) - 1
+                if last and self.emit_point_major and y.is_contiguous() and y.shape[0] <= 65535:
+                    pm = torch.empty(y.shape[0], y.shape[2], y.shape[1], dtype=torch.float16, device=y.device)
+                    rc = L.g4d_bias_relu_pm(y.shape[0], y.shape[1], y.shape[2], _lib.ptr(y), _lib.ptr(b), 1, _lib.ptr(pm), _lib.stream_ptr())
+                    _lib.check(rc, "g4d_bias_relu_pm")
+                    y._g4d_pm = pm
+                elif y.shape[0] * y.shape[1] <= 65535 and y.is_contiguous():
                     rc = L.g4d_bias_relu_inplace(y.shape[0], y.shape[1], y.shape[2], _lib.ptr(y), _lib.ptr(b), 1, _lib.stream_ptr())
                     _lib.check(rc, "g4d_bias_relu_inplace")
                 else:
@@ -232,8 +255,11 @@ class PointnetFPModule(nn.Module):
             return y
         return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
 
-    def _folded_mlp(self, x):
-        if self.training or not x.is_cuda or (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.mlp.parameters()))):
+    emit_point_major = False      # set by the encoder on the level that feeds the fused finest-level kernel
+
+    def _folded_mlp(self, x, skip=None):
+        if self.training or not x.is_cuda or (torch.is_grad_enabled() and (x.requires_grad or (skip is not None and skip.requires_grad)
+                                                                           or any(p.requires_grad for p in self.mlp.parameters()))):
             return None
         ver = pt_utils.shared_mlp_version(self.mlp)
         hit = getattr(self, "_fold_cache", None)

@@ -163,6 +163,17 @@ int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int b, int n
  * epilogue for the feature-propagation 1x1 convolutions that stay on the library GEMM (pointnet2_modules.py:154). */
 int g4d_bias_relu_inplace(int b, int c, long long n, float* y, const float* bias, int relu, void* stream);
 
+/* Front half of PointnetFPModule.forward (pointnet2_modules.py:138-152) in one pass: inverse-distance weights from
+ * three_nn's SQUARED distances (1/(sqrt(d2)+1e-8), normalised; bit-identical to the torch expression), three_interpolate
+ * of known_feats (b,c2,m) and the concatenation with the skip features skip (b,c1,n) (NULL with c1 = 0):
+ * out (b, c2+c1, n) = cat([interpolated, skip], dim=1).  Replaces 5 torch kernels + three_interpolate + torch.cat. */
+int g4d_fp_interp_concat(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const float* known_feats,
+                         const float* skip, float* out, void* stream);
+
+/* g4d_bias_relu_inplace that ALSO writes the activated values as fp16 point-major out_pm (b,n,c): the gather layout of
+ * g4d_fp_interp_mlp / g4d_sa_mlp_max (replaces transpose(1,2).to(half).contiguous() on the next level's input). */
+int g4d_bias_relu_pm(int b, int c, int n, float* y, const float* bias, int relu, void* out_pm, void* stream);
+
 /* ---- 3. SMPL linear-blend skinning (smplx/smplx/lbs.py) ----------------------------------------- */
 
 /* batch_rodrigues (lbs.py:312-346): rot_vecs (n,3) -> rot_mats (n,3,3) */

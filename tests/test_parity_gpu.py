@@ -238,3 +238,54 @@ def test_grid_searches_equal_brute_force(cuda, shape):
     d, i = pu.three_nn((x + 0.3).contiguous(), new_xyz)
     d2b, ib = _brute_nn((x + 0.3).contiguous(), new_xyz)
     assert torch.equal(i, ib) and torch.equal(d, torch.sqrt(d2b))
+
+
+@pytest.mark.parametrize("case", [(41, 2, 1024, 256, 256, 96), (42, 3, 256, 64, 384, 192), (43, 2, 1000, 77, 20, 0), (44, 1, 300, 5, 3, 7)],
+                         ids=lambda c: f"n{c[2]}m{c[3]}c{c[4]}+{c[5]}")
+def test_fp_interp_concat_vs_operator_sequence(cuda, case):
+    """g4d_fp_interp_concat == the reference's operator sequence of PointnetFPModule.forward (pointnet2_modules.py:138-152):
+    three_nn -> 1/(dist+1e-8) -> normalise -> three_interpolate -> cat, run here through torch + the 1:1 operators."""
+    import ctypes
+    from garment4d_b200 import _lib
+    seed, B, n, m, c2, c1 = case
+    unknown = clouds(seed, B, n, "body", dup_frac=0.02)       # duplicates: zero distances exercise the 1e-8 term
+    known = unknown[:, :m].copy()
+    rs = np.random.RandomState(seed)
+    u, k = _t(unknown, cuda), _t(known, cuda)
+    kf = _t(rs.randn(B, c2, m).astype(np.float32), cuda)
+    skip = _t(rs.randn(B, c1, n).astype(np.float32), cuda) if c1 else None
+    dist, idx = pu.three_nn(u, k)
+    dist_recip = 1.0 / (dist + 1e-8)
+    weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+    want = pu.three_interpolate(kf, idx, weight)
+    if skip is not None:
+        want = torch.cat([want, skip], dim=1)
+    dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=cuda)
+    idx2 = torch.empty(B, n, 3, dtype=torch.int32, device=cuda)
+    pu.three_nn_raw(u, k, dist2, idx2)
+    assert torch.equal(idx2, idx)
+    out = torch.full((B, c2 + c1, n), float("nan"), dtype=torch.float32, device=cuda)
+    rc = _lib.lib().g4d_fp_interp_concat(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx2), _lib.ptr(kf), _lib.ptr(skip), _lib.ptr(out),
+                                         _lib.stream_ptr())
+    _lib.check(rc, "g4d_fp_interp_concat")
+    assert torch.isfinite(out).all()
+    if c1:
+        assert torch.equal(out[:, c2:], skip), "skip channels must be copied verbatim"
+    # weights: same correctly rounded operations; torch's 3-term sum may associate differently -> 2 ulp of slack on the output
+    np.testing.assert_allclose(out[:, :c2].cpu().numpy(), want[:, :c2].cpu().numpy(), rtol=5e-7, atol=1e-7 * float(kf.abs().max()))
+
+
+def test_bias_relu_pm(cuda):
+    """g4d_bias_relu_pm: in-place bias+ReLU (== g4d_bias_relu_inplace) plus the fp16 point-major copy."""
+    from garment4d_b200 import _lib
+    rs = np.random.RandomState(51)
+    for (B, C, n) in [(2, 128, 1024), (3, 50, 77), (1, 7, 5)]:
+        y0 = _t(rs.randn(B, C, n).astype(np.float32) * 3, cuda)
+        b = _t(rs.randn(C).astype(np.float32), cuda)
+        y = y0.clone()
+        pm = torch.zeros(B, n, C, dtype=torch.float16, device=cuda)
+        rc = _lib.lib().g4d_bias_relu_pm(B, C, n, _lib.ptr(y), _lib.ptr(b), 1, _lib.ptr(pm), _lib.stream_ptr())
+        _lib.check(rc, "g4d_bias_relu_pm")
+        want = torch.relu(y0 + b[None, :, None])
+        assert torch.equal(y, want)
+        assert torch.equal(pm, want.transpose(1, 2).to(torch.float16).contiguous())
