@@ -325,27 +325,46 @@ def kernel_breakdown(torch, L, model, pc, betas, pose, smpl, flush, peaks, C, N,
             tot += s.elapsed_time(e)
         return tot / reps
 
-    def hbm(name, ms, bytes_per_cloud, note=""):
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the same c3-sized launch, from the committed
+    # `ncu --set full` capture (profiles/*_ncu_summary.json, written by tools/summarize_ncu.py); None when not captured.
+    ncu_rows = []
+    if C == 240 and N == 8192:
+        import glob
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_summary.json")))
+        if cands:
+            ncu_rows = json.load(open(cands[-1]))
+
+    def traffic(key):
+        if key is None:
+            return None
+        sub, occ = key
+        hits = [r for r in ncu_rows if sub in r["kernel"]]
+        return hits[occ]["traffic_bytes"] if occ < len(hits) else None
+
+    def hbm(name, ms, bytes_per_cloud, note="", ncu=None):
         ach = bytes_per_cloud * C / (ms * 1e-3) / 1e9
         out.append({"name": name, "ms": ms, "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                         "frac": ach / peaks["hbm_gbs"], "traffic": None}, "note": note})
+                                                         "frac": ach / peaks["hbm_gbs"], "traffic": traffic(ncu)}, "note": note})
 
-    def tensor(name, ms, macs_per_cloud):
+    def tensor(name, ms, macs_per_cloud, ncu=None):
         ach = 2.0 * macs_per_cloud * C / (ms * 1e-3) / 1e12
         out.append({"name": name, "ms": ms, "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tc_tflops"], "unit": "TFLOP/s",
-                                                         "frac": ach / peaks["tc_tflops"], "traffic": None}})
+                                                         "frac": ach / peaks["tc_tflops"], "traffic": traffic(ncu)}})
 
     with torch.no_grad():
         xyz, feats = pc.contiguous(), None
+        lx, lf = [xyz], [None]
         for lvl, sa in enumerate(model.SA_modules):
             n_in, P = xyz.shape[1], sa.npoint
             ms = t(lambda: pu.furthest_point_sample_and_gather(xyz, P))
             hbm(f"fps_gather L{lvl} ({n_in}->{P})", ms, 12 * n_in + 16 * P,
-                note=f"serial ALU chain: {10 * n_in * (P - 1) * C / (ms * 1e-3) / 1e12:.2f} T lane-ops/s of 37.2 peak")
+                note=f"serial ALU chain: {10 * n_in * (P - 1) * C / (ms * 1e-3) / 1e12:.2f} T lane-ops/s of 37.2 peak",
+                ncu=(("fps_pruned_kernel<512", 0), ("fps_kernel<256, 4", 0), ("fps_kernel<256, 1", 0))[lvl] if lvl < 3 else None)
             _, new_xyz = pu.furthest_point_sample_and_gather(xyz, P)
             g0, g1 = sa.groupers
             ms = t(lambda: pu.ball_query_pair(g0.radius, g0.nsample, g1.radius, g1.nsample, xyz, new_xyz))
-            hbm(f"ball_query2 L{lvl}", ms, 12 * n_in + 12 * P + 4 * P * (g0.nsample + g1.nsample))
+            hbm(f"ball_query2 L{lvl}", ms, 12 * n_in + 12 * P + 4 * P * (g0.nsample + g1.nsample),
+                ncu=("ball_query_grid_kernel<2>", 0) if lvl == 0 else ("ball_query_kernel<2>", lvl - 1))
             idxs = pu.ball_query_pair(g0.radius, g0.nsample, g1.radius, g1.nsample, xyz, new_xyz)
             c_in = 0 if feats is None else feats.shape[1]
             # the north star's fused ball-query+group operator (materialises the grouped tensor; not on the fused route)
@@ -368,9 +387,32 @@ def kernel_breakdown(torch, L, model, pc, betas, pose, smpl, flush, peaks, C, N,
                 ms = t(run)
                 d = br.desc
                 tensor(f"sa_mlp_max L{lvl} K={g.nsample} ({c_in}+3->{d.c1},{d.c2},{d.c3})", ms,
-                       branch_macs(g.nsample, c_in, (d.c1, d.c2, d.c3), P))
+                       branch_macs(g.nsample, c_in, (d.c1, d.c2, d.c3), P),
+                       ncu=(f"sa_mlp_max_kernel<{g.nsample}, {1 if c_in else 0}, ", 1 if (lvl == 2 and g.nsample == 32) else 0))
                 off += br.c_out
             xyz, feats = new_xyz2, new_feats
+            lx.append(xyz); lf.append(feats)
+        # feature propagation: FP2 / FP1 modules (our prologue + library GEMMs + our epilogues), then the fused finest level + head
+        from garment4d_b200.pointnet2 import pointnet2_cuda_bridge as bridge
+        fp2, fp1 = model.FP_modules[2], model.FP_modules[1]
+        ms = t(lambda: fp2(lx[2], lx[3], lf[2], lf[3]))
+        f2 = fp2(lx[2], lx[3], lf[2], lf[3])
+        out.append({"name": "FP2 module (three_nn + interp/concat kernel + 2 library GEMMs + bias/ReLU kernels)", "ms": ms})
+        ms = t(lambda: fp1(lx[1], lx[2], lf[1], f2))
+        f1 = fp1(lx[1], lx[2], lf[1], f2)
+        out.append({"name": "FP1 module (three_nn + interp/concat kernel + 2 library GEMMs + bias/ReLU(+fp16 point-major) kernels)", "ms": ms})
+        d2 = torch.empty(C, N, 3, dtype=torch.float32, device=pc.device)
+        i3 = torch.empty(C, N, 3, dtype=torch.int32, device=pc.device)
+        ms_nn = t(lambda: pu.three_nn_raw(lx[0], lx[1], d2, i3))
+        hbm(f"three_nn L0 ({N} -> {lx[1].shape[1]}, grid)", ms_nn, 12 * N + 12 * lx[1].shape[1] + 24 * N, ncu=("three_nn_grid_kernel", 0))
+        if model._fused_fp0_head(lx, [None, f1, f2, lf[3]]) is not None:
+            packed = model._fp0_cache[str(pc.device)][1]
+            ms = t(lambda: bridge.fp_interp_mlp(packed, lx[0], lx[1], f1)) - ms_nn
+            d = packed.desc
+            hbm(f"fp_interp_mlp ({d.c_in}->{d.c1},{d.c2} + head {d.h1},{d.h2}; tcgen05)", ms,
+                4 * d.c2 * N + 4 * d.h2 * N + 24 * N + 2 * d.c_in * lx[1].shape[1],
+                note=f"{2.0 * N * (d.c_in * d.c1 + d.c1 * d.c2 + d.c2 * d.h1 + d.h1 * 16) * C / (ms * 1e-3) / 1e12:.1f} TFLOP/s on the tensor pipe",
+                ncu=("fp_interp_mlp_kernel", 0))
         ms = t(lambda: glbs.lbs(betas, pose, *smpl))
         hbm("lbs (6 kernels)", ms, 83872, note=f"{2 * 7737470 * C / (ms * 1e-3) / 1e12:.2f} TFLOP/s fp32 of ~74.5 FFMA peak")
         ms_sa = t(lambda: model.sa_stack(pc))

@@ -6,11 +6,22 @@
 //     three_interpolate                                                                     interpolate_gpu.cu:77-97
 //     unsqueeze ; 2 x [cuDNN conv1x1 -> BatchNorm2d -> ReLU] ; squeeze                      pytorch_utils.py:5-32
 //     Conv1d(64,32)+BN+ReLU ; Dropout (eval: identity) ; Conv1d(32,classes) ; transpose     pointnet2encoder.py:98-101,143
-// (~16 kernels, each streaming a (B, C, N) activation of up to 1 GB through HBM at c3) with ONE persistent kernel:
-// per 128-point tile the 3-tap interpolation is evaluated while gathering (fp32, the reference's FMUL/FFMA order),
-// written as fp16 in the UMMA canonical layout, and up to four chained tcgen05.mma layers run with fp32 TMEM
-// accumulators; only the FP output (channel-major fp32, returned by the encoder as l_features[0]) and the logits
-// (point-major) are written to HBM.
+// (~16 kernels, each streaming a (B, C, N) activation of up to 1 GB through HBM at c3) with ONE persistent,
+// warp-specialised kernel (one CTA per SM, 16 warps):
+//
+//   producer groups (2 x 4 warps)  take alternate 128-point tiles: inverse-distance weights from three_nn's squared
+//                                  distances (meta loads prefetched one tile ahead), then the 3-tap interpolation is
+//                                  evaluated while gathering the fp16 point-major rows (24 x 16-byte loads in flight per
+//                                  lane; fp32 arithmetic in the reference's FMUL/FFMA order) and written as fp16 in the
+//                                  UMMA canonical layout into a ring of A buffers (full/empty mbarriers).
+//   consumer groups (2 x 4 warps)  take alternate tiles, each with its own TMEM accumulator (128 columns) and hidden
+//                                  buffer: one lane issues the tcgen05.mma chain (up to four layers), the group's four
+//                                  warps run the epilogues (tcgen05.ld -> bias, ReLU -> fp16 -> shared; layer 2 also
+//                                  writes the FP output, the last layer the logits).  The A buffer is released by the
+//                                  tcgen05.commit of layer 1, so the gather of the following tiles overlaps the chain.
+//   Only the FP output (channel-major fp32, returned by the encoder as l_features[0]) and the logits (point-major)
+//   are written to HBM.  (The first version ran gather and layers back to back in one 256-thread CTA with block-wide
+//   barriers: 31 % of its warp samples waited on the gather, 31 % at barriers -- profiles/r01_ncu_summary.md.)
 #include <string.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -19,12 +30,14 @@
 namespace g4d {
 
 constexpr int FP_TILE = 128;
-constexpr int FP_THREADS = 256;     // warps 0-3: rows / TMEM lanes (weights, epilogues); all 8 warps gather
+constexpr int FP_CG = 2, FP_PG = 2;                   // consumer / producer groups of 4 warps each
+constexpr int FP_THREADS = (FP_CG + FP_PG) * 128;     // warps [0, 4*FP_CG): consumers; the rest: producers
+constexpr int FP_MAX_A = 4;                           // A-buffer ring depth (as many as fit, at least 2)
 
 struct FpLayout {
     int c_in, c1, c2, h1, h2, h2p;      // h2p = 16 when a head is present (classes padded), else 0
     uint32_t off_w1, off_w2, off_w3, off_w4, off_b1, off_b2, off_b3, off_b4, blob_bytes;
-    uint32_t off_act, off_meta, off_bar, total_smem, tmem_cols;
+    uint32_t off_a, a_bytes, na, off_h, h_bytes, off_meta, off_bar, total_smem, tcols, tmem_cols;
 };
 
 static bool fp_layout(const g4d_fp_desc* d, FpLayout* L, const char** why) {
@@ -42,20 +55,24 @@ static bool fp_layout(const g4d_fp_desc* d, FpLayout* L, const char** why) {
     L->off_b3 = o; o += (uint32_t)L->h1 * 4;
     L->off_b4 = o; o += (uint32_t)L->h2p * 4;
     L->blob_bytes = o;
-    int kmax = L->c_in;
-    if (L->c1 > kmax) kmax = L->c1;
-    if (L->c2 > kmax) kmax = L->c2;
-    if (L->h1 > kmax) kmax = L->h1;
-    L->off_act = (o + 127) / 128 * 128;
-    L->off_meta = L->off_act + (uint32_t)FP_TILE * kmax * 2;
-    L->off_bar = L->off_meta + FP_TILE * 6 * 4;           // 3 point ids + 3 weights per row
-    L->total_smem = L->off_bar + 64;
-    uint32_t cols = L->c1 > L->c2 ? L->c1 : L->c2;
-    if ((uint32_t)L->h1 > cols) cols = L->h1;
+    int hmax = L->c1;                                      // widest hidden activation (K of layers 2..4)
+    if (L->c2 > hmax) hmax = L->c2;
+    if (L->h1 > hmax) hmax = L->h1;
+    L->a_bytes = (uint32_t)FP_TILE * L->c_in * 2;
+    L->h_bytes = (uint32_t)FP_TILE * hmax * 2;
+    L->off_h = (o + 127) / 128 * 128;
+    L->off_meta = L->off_h + FP_CG * L->h_bytes;           // per producer group, double-buffered: 3 point ids + 3 weights per row
+    L->off_bar = L->off_meta + FP_PG * 2 * FP_TILE * 6 * 4;
+    L->off_a = (L->off_bar + 8 * (3 + 2 * FP_MAX_A + FP_CG) + 127) / 128 * 128;
+    const uint32_t budget = 227u * 1024u;
+    if (L->off_a + 2 * L->a_bytes > budget) { *why = "fp: shared memory footprint exceeds 227 KB"; return false; }
+    uint32_t na = (budget - L->off_a) / L->a_bytes;
+    L->na = na > (uint32_t)FP_MAX_A ? (uint32_t)FP_MAX_A : na;
+    L->total_smem = L->off_a + L->na * L->a_bytes;
     uint32_t p2 = 32;
-    while (p2 < cols) p2 <<= 1;
-    L->tmem_cols = p2;
-    if (L->total_smem > 227 * 1024) { *why = "fp: shared memory footprint exceeds 227 KB"; return false; }
+    while (p2 < (uint32_t)hmax || p2 < (uint32_t)L->h2p) p2 <<= 1;
+    L->tcols = p2;                                         // accumulator columns per consumer group
+    L->tmem_cols = p2 * FP_CG;                             // <= 512
     return true;
 }
 
@@ -78,8 +95,8 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
     for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
-// TMEM row -> +bias, ReLU, fp16 -> act buffer (canonical layout), optionally also fp32 channel-major to global
-__device__ __forceinline__ void fp_epilogue_relu(uint32_t lane_taddr, int ncols, const float* bias, unsigned char* act, int tid,
+// TMEM row -> +bias, ReLU, fp16 -> hidden buffer (canonical layout), optionally also fp32 channel-major to global
+__device__ __forceinline__ void fp_epilogue_relu(uint32_t lane_taddr, int ncols, const float* bias, unsigned char* hbuf, int row,
                                                  float* gout /* channel 0 of this row's point, or null */, size_t gstride) {
     for (int c0 = 0; c0 < ncols; c0 += 16) {
         float v[16];
@@ -93,175 +110,223 @@ __device__ __forceinline__ void fp_epilogue_relu(uint32_t lane_taddr, int ncols,
         uint32_t h[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) h[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
-        uint4* dst = reinterpret_cast<uint4*>(act);
-        dst[(size_t)(c0 / 8) * FP_TILE + tid] = make_uint4(h[0], h[1], h[2], h[3]);
-        dst[(size_t)(c0 / 8 + 1) * FP_TILE + tid] = make_uint4(h[4], h[5], h[6], h[7]);
+        uint4* dst = reinterpret_cast<uint4*>(hbuf);
+        dst[(size_t)(c0 / 8) * FP_TILE + row] = make_uint4(h[0], h[1], h[2], h[3]);
+        dst[(size_t)(c0 / 8 + 1) * FP_TILE + row] = make_uint4(h[4], h[5], h[6], h[7]);
     }
 }
 
-__device__ __forceinline__ void fp_issue_layer(uint32_t tmem, uint32_t s_act, uint32_t s_w, int K, int N, uint32_t bar) {
+// D[128 x N] (+)= A[128 x K] . W[N x K]^T, one tcgen05.mma per 16-wide K step (issued by ONE thread; descriptors advance
+// by plain 32-bit adds on their low words: every instruction on this lane's path is latency of the whole chain)
+__device__ __forceinline__ void fp_issue_layer(uint32_t tmem, uint32_t s_act, uint32_t s_w, int K, int N) {
     tc_fence_after();
     const uint32_t idesc = umma_idesc(FP_TILE, N);
-    for (int k = 0; k < K / 16; ++k) {
-        const uint64_t ad = umma_desc(s_act + (uint32_t)k * 2 * FP_TILE * 16, FP_TILE * 16, 128);
-        const uint64_t bd = umma_desc(s_w + (uint32_t)k * 2 * N * 16, N * 16, 128);
-        umma_f16(tmem, ad, bd, idesc, k > 0);
+    uint32_t alo = desc_lo(s_act, FP_TILE * 16), blo = desc_lo(s_w, (uint32_t)N * 16);
+    const uint32_t a_step = (uint32_t)(2 * FP_TILE * 16) >> 4, b_step = (uint32_t)(2 * N * 16) >> 4;
+    const int ks = K >> 4;
+#pragma unroll 1
+    for (int k = 0; k < ks; ++k) {
+        umma_f16(tmem, desc64(alo), desc64(blo), idesc, k > 0);
+        alo += a_step; blo += b_step;
     }
-    umma_commit(bar);
 }
 
-__global__ void __launch_bounds__(FP_THREADS)
+__device__ __forceinline__ void group_bar(int id) {          // the 128 threads of one consumer / producer group
+    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
+
+__global__ void __launch_bounds__(FP_THREADS, 1)
 fp_interp_mlp_kernel(const FpArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const FpLayout& L = a.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char* act = smem + L.off_act;
-    uint32_t* rowpt = reinterpret_cast<uint32_t*>(smem + L.off_meta);          // [3][128]
-    float* roww = reinterpret_cast<float*>(smem + L.off_meta + FP_TILE * 3 * 4); // [3][128]
     const float* b1 = reinterpret_cast<const float*>(smem + L.off_b1);
     const float* b2 = reinterpret_cast<const float*>(smem + L.off_b2);
     const float* b3 = reinterpret_cast<const float*>(smem + L.off_b3);
     const float* b4 = reinterpret_cast<const float*>(smem + L.off_b4);
-    const uint32_t bar_w = smem_u32(smem + L.off_bar), bar_mma = bar_w + 8, tmem_slot = bar_w + 16;
-    const uint32_t s_act = smem_u32(act);
-    const uint32_t s_w1 = smem_u32(smem + L.off_w1), s_w2 = smem_u32(smem + L.off_w2), s_w3 = smem_u32(smem + L.off_w3),
-                   s_w4 = smem_u32(smem + L.off_w4);
+    // barriers: [0] weights, [1] tmem slot, [2 .. 2+MAX_A) full[a], [2+MAX_A .. 2+2*MAX_A) empty[a], then mma_done[group]
+    const uint32_t bar0 = smem_u32(smem + L.off_bar);
+    const uint32_t bar_w = bar0, tmem_slot = bar0 + 8, bar_full = bar0 + 16, bar_empty = bar_full + 8 * FP_MAX_A,
+                   bar_done = bar_empty + 8 * FP_MAX_A;
+    const int NA = (int)L.na;
 
     if (tid == 0) {
         mbar_init(bar_w, 1);
-        mbar_init(bar_mma, 1);
+        for (int i = 0; i < NA; ++i) { mbar_init(bar_full + 8 * i, 4); /* the 4 warps of the filling producer group */ mbar_init(bar_empty + 8 * i, 1); }
+        for (int g = 0; g < FP_CG; ++g) mbar_init(bar_done + 8 * g, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(tmem_slot, L.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L.off_bar + 16);
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + L.off_bar + 8);
     if (tid == 0) {
         mbar_expect_tx(bar_w, L.blob_bytes);
         bulk_g2s(smem_u32(smem), a.params, L.blob_bytes, bar_w);
     }
-    mbar_wait(bar_w, 0);
+    const int nseq = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // tiles of this CTA: blockIdx.x + i * gridDim.x
 
-    const int nchunk = L.c_in >> 3;
-    const uint32_t lane_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t phase = 0;
-
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const long long R = (long long)tile * FP_TILE + (tid & (FP_TILE - 1));
-        const bool live = R < a.total_rows && tid < FP_TILE;
-        const unsigned cloud = live ? (unsigned)((unsigned long long)R / (unsigned)a.n) : 0u;   // total_rows < 2^32 * n: one 64/32 division
-        const int pt = live ? (int)(R - (long long)cloud * a.n) : 0;
-        // ---- interpolation weights, exactly the reference's torch arithmetic (pointnet2_modules.py:141-143) ----
-        {
-            uint32_t p0 = 0xFFFFFFFFu, p1 = 0xFFFFFFFFu, p2 = 0xFFFFFFFFu;
-            float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-            if (live) {
-                const float* d2 = a.dist2 + (size_t)R * 3;
-                const int* id = a.idx + (size_t)R * 3;
-                const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2)), 1e-8f));
-                const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 1)), 1e-8f));
-                const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 2)), 1e-8f));
-                const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
-                w0 = __fdiv_rn(r0, norm); w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm);
-                const uint32_t base = cloud * (uint32_t)a.m;
-                p0 = base + (uint32_t)__ldg(id); p1 = base + (uint32_t)__ldg(id + 1); p2 = base + (uint32_t)__ldg(id + 2);
-            }
-            if (tid < FP_TILE) {
-                rowpt[tid] = p0; rowpt[FP_TILE + tid] = p1; rowpt[2 * FP_TILE + tid] = p2;
-                roww[tid] = w0; roww[FP_TILE + tid] = w1; roww[2 * FP_TILE + tid] = w2;
-            }
+    if (warp >= 4 * FP_CG) {
+        // =========================== PRODUCERS ==================================================================
+        const int pg = (warp - 4 * FP_CG) >> 2;                 // producer group
+        const int pw = (warp - 4 * FP_CG) & 3;                  // warp within the group: tile rows 32*pw .. 32*pw+31
+        const int prow = pw * 32 + lane;                         // the row whose meta data this thread prepares
+        const int rl = lane & 7, cl = lane >> 3;
+        const int nchunk = L.c_in >> 3;
+        uint32_t* meta = reinterpret_cast<uint32_t*>(smem + L.off_meta) + pg * 2 * (FP_TILE * 6);
+        // meta loads of the first tile of this group
+        float d0 = 0.f, d1 = 0.f, d2v = 0.f;
+        int j0 = 0, j1 = 0, j2 = 0;
+        long long Rn = ((long long)blockIdx.x + (long long)pg * gridDim.x) * FP_TILE + prow;
+        if (pg < nseq && Rn < a.total_rows) {
+            const float* dp = a.dist2 + (size_t)Rn * 3; const int* ip = a.idx + (size_t)Rn * 3;
+            d0 = __ldg(dp); d1 = __ldg(dp + 1); d2v = __ldg(dp + 2); j0 = __ldg(ip); j1 = __ldg(ip + 1); j2 = __ldg(ip + 2);
         }
-        __syncthreads();
-        // ---- gather + interpolate (all 8 warps) ----
-        {
-            const int rl = lane & 7, cl = lane >> 3;
-            uint4* dst = reinterpret_cast<uint4*>(act);
-            // warp w (of 8) owns rows 16w..16w+15 = 2 groups of 8 rows; 4 chunks per lane per group; the 24 loads of both
-            // groups (3 taps x 4 chunks x 2) are issued before the first use: the gather is pure L2/HBM latency
-            uint32_t q[2][3];
-            float wt[2][3];
-            const uint4* sp[2][3];
-#pragma unroll
-            for (int rg = 0; rg < 2; ++rg) {
-                const int row = warp * 16 + rg * 8 + rl;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    q[rg][k] = rowpt[k * FP_TILE + row];
-                    wt[rg][k] = roww[k * FP_TILE + row];
-                    sp[rg][k] = reinterpret_cast<const uint4*>(a.known_pm + (size_t)q[rg][k] * L.c_in);
+        int buf = 0;
+        for (int i = pg; i < nseq; i += FP_PG, buf ^= 1) {
+            const long long R = Rn;
+            const bool live = R < a.total_rows;
+            // ---- interpolation weights of row `prow`, exactly the reference's torch arithmetic (pointnet2_modules.py:141-143)
+            uint32_t* rowpt = meta + buf * (FP_TILE * 6);
+            float* roww = reinterpret_cast<float*>(rowpt + FP_TILE * 3);
+            {
+                uint32_t p0 = 0xFFFFFFFFu, p1 = 0xFFFFFFFFu, p2 = 0xFFFFFFFFu;
+                float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+                if (live) {
+                    const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d0), 1e-8f));
+                    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d1), 1e-8f));
+                    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d2v), 1e-8f));
+                    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+                    w0 = __fdiv_rn(r0, norm); w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm);
+                    const uint32_t base = (uint32_t)((unsigned long long)R / (unsigned)a.n) * (uint32_t)a.m;
+                    p0 = base + (uint32_t)j0; p1 = base + (uint32_t)j1; p2 = base + (uint32_t)j2;
                 }
+                rowpt[prow] = p0; rowpt[FP_TILE + prow] = p1; rowpt[2 * FP_TILE + prow] = p2;
+                roww[prow] = w0; roww[FP_TILE + prow] = w1; roww[2 * FP_TILE + prow] = w2;
             }
-            for (int cb = cl; cb < nchunk; cb += 16) {
-                uint4 ld[2][3][4];
-#pragma unroll
-                for (int rg = 0; rg < 2; ++rg)
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int c = cb + 4 * u;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            ld[rg][k][u] = make_uint4(0, 0, 0, 0);
-                            if (c < nchunk && q[rg][0] != 0xFFFFFFFFu) ld[rg][k][u] = __ldg(sp[rg][k] + c);
-                        }
-                    }
+            group_bar(1 + FP_CG + pg);          // meta[buf] complete (it is rewritten two tiles later, after the next barrier)
+            // ---- prefetch the meta loads of this group's next tile: their latency hides behind the gather
+            Rn = R + (long long)FP_PG * gridDim.x * FP_TILE;
+            if (i + FP_PG < nseq && Rn < a.total_rows) {
+                const float* dp = a.dist2 + (size_t)Rn * 3; const int* ip = a.idx + (size_t)Rn * 3;
+                d0 = __ldg(dp); d1 = __ldg(dp + 1); d2v = __ldg(dp + 2); j0 = __ldg(ip); j1 = __ldg(ip + 1); j2 = __ldg(ip + 2);
+            }
+            // ---- A buffer of this tile
+            const int ab = i % NA;
+            const uint32_t use = (uint32_t)(i / NA);
+            mbar_wait(bar_empty + 8 * ab, (use & 1) ^ 1);       // freed by the commit of layer 1 of tile i - NA (first lap passes)
+            uint4* dst = reinterpret_cast<uint4*>(smem + L.off_a + (size_t)ab * L.a_bytes);
+            // ---- gather + interpolate: warp pw owns rows 32pw..32pw+31 in two rounds of 16 rows = 2 groups of 8 rows;
+            //      4 chunks per lane per group; the 24 loads of a round are issued before their first use
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint32_t q[2][3];                                // chunk index of the tap's row start (point id * chunks per row)
+                float wt[2][3];
+                bool valid[2];
+                const uint4* kp = reinterpret_cast<const uint4*>(a.known_pm);
 #pragma unroll
                 for (int rg = 0; rg < 2; ++rg) {
-                    const int row = warp * 16 + rg * 8 + rl;
+                    const int row = pw * 32 + h * 16 + rg * 8 + rl;
+                    valid[rg] = rowpt[row] != 0xFFFFFFFFu;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int c = cb + 4 * u;
-                        if (c < nchunk) {
-                            float f0[8], f1[8], f2[8], r[8];
-                            unpack8(ld[rg][0][u], f0); unpack8(ld[rg][1][u], f1); unpack8(ld[rg][2][u], f2);
+                    for (int k = 0; k < 3; ++k) {
+                        q[rg][k] = valid[rg] ? rowpt[k * FP_TILE + row] * (uint32_t)nchunk : 0u;      // b*m*c_in/8 < 2^32 (host check)
+                        wt[rg][k] = roww[k * FP_TILE + row];
+                    }
+                }
+#pragma unroll 1
+                for (int cb = cl; cb < nchunk; cb += 16) {
+                    uint4 ld[2][3][4];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)     // interpolate_gpu.cu:96 in the reference build's order
-                                r[i] = __fmaf_rn(wt[rg][2], f2[i], __fmaf_rn(wt[rg][0], f0[i], __fmul_rn(wt[rg][1], f1[i])));
-                            uint4 o = make_uint4(0, 0, 0, 0);
-                            if (q[rg][0] != 0xFFFFFFFFu)
-                                o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
-                            dst[(size_t)c * FP_TILE + row] = o;
+                    for (int rg = 0; rg < 2; ++rg)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int c = cb + 4 * u;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                ld[rg][k][u] = make_uint4(0, 0, 0, 0);
+                                if (c < nchunk && valid[rg]) ld[rg][k][u] = __ldg(kp + (q[rg][k] + (uint32_t)c));
+                            }
+                        }
+#pragma unroll
+                    for (int rg = 0; rg < 2; ++rg) {
+                        const int row = pw * 32 + h * 16 + rg * 8 + rl;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int c = cb + 4 * u;
+                            if (c < nchunk) {
+                                float f0[8], f1[8], f2[8], r[8];
+                                unpack8(ld[rg][0][u], f0); unpack8(ld[rg][1][u], f1); unpack8(ld[rg][2][u], f2);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e)     // interpolate_gpu.cu:96 in the reference build's order
+                                    r[e] = __fmaf_rn(wt[rg][2], f2[e], __fmaf_rn(wt[rg][0], f0[e], __fmul_rn(wt[rg][1], f1[e])));
+                                uint4 o = make_uint4(0, 0, 0, 0);
+                                if (valid[rg])
+                                    o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
+                                dst[(size_t)c * FP_TILE + row] = o;
+                            }
                         }
                     }
                 }
             }
+            fence_proxy_async();                                 // generic-proxy stores -> visible to tcgen05.mma
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * ab);
         }
-        fence_proxy_async();
-        __syncthreads();
-
-        // ---- layer 1 ----
-        if (tid == 0) fp_issue_layer(tmem, s_act, s_w1, L.c_in, L.c1, bar_mma);
-        if (warp < 4) {
-            mbar_wait(bar_mma, phase);
-            tc_fence_after();
-            fp_epilogue_relu(lane_taddr, L.c1, b1, act, tid, nullptr, 0);
-        }
-        phase ^= 1;
-        tc_fence_before(); fence_proxy_async(); __syncthreads();
-        // ---- layer 2 (FP output) ----
-        if (tid == 0) fp_issue_layer(tmem, s_act, s_w2, L.c1, L.c2, bar_mma);
-        if (warp < 4) {
-            mbar_wait(bar_mma, phase);
-            tc_fence_after();
-            fp_epilogue_relu(lane_taddr, L.c2, b2, act, tid, live ? a.out_feat + ((size_t)cloud * L.c2) * a.n + pt : nullptr, (size_t)a.n);
-        }
-        phase ^= 1;
-        tc_fence_before(); fence_proxy_async(); __syncthreads();
-        if (L.h1) {
-            // ---- head layer 1 ----
-            if (tid == 0) fp_issue_layer(tmem, s_act, s_w3, L.c2, L.h1, bar_mma);
-            if (warp < 4) {
-                mbar_wait(bar_mma, phase);
-                tc_fence_after();
-                fp_epilogue_relu(lane_taddr, L.h1, b3, act, tid, nullptr, 0);
+    } else {
+        // =========================== CONSUMERS ==================================================================
+        const int cg = warp >> 2;                                // consumer group; its warps own TMEM lane quadrants warp & 3
+        const int row = (warp & 3) * 32 + lane;                  // tile row == TMEM lane
+        const bool issuer = (warp & 3) == 0 && lane == 0;
+        const uint32_t tacc = tmem + (uint32_t)cg * L.tcols;     // this group's accumulator columns
+        const uint32_t lane_taddr = tacc + ((uint32_t)((warp & 3) * 32) << 16);
+        unsigned char* hbuf = smem + L.off_h + (size_t)cg * L.h_bytes;
+        const uint32_t s_h = smem_u32(hbuf);
+        const uint32_t s_w1 = smem_u32(smem + L.off_w1), s_w2 = smem_u32(smem + L.off_w2), s_w3 = smem_u32(smem + L.off_w3),
+                       s_w4 = smem_u32(smem + L.off_w4);
+        const uint32_t my_done = bar_done + 8 * cg;
+        const int bar_id = 1 + cg;
+        uint32_t phase = 0;
+        mbar_wait(bar_w, 0);                                     // weights + biases resident
+        for (int i = cg; i < nseq; i += FP_CG) {
+            const long long R = ((long long)blockIdx.x + (long long)i * gridDim.x) * FP_TILE + row;
+            const bool live = R < a.total_rows;
+            const unsigned cloud = live ? (unsigned)((unsigned long long)R / (unsigned)a.n) : 0u;
+            const int pt = live ? (int)(R - (long long)cloud * a.n) : 0;
+            const int ab = i % NA;
+            const uint32_t use = (uint32_t)(i / NA);
+            // ---- layer 1: A buffer -> D ; its commit releases the A buffer to the producers
+            if (issuer) {
+                mbar_wait_spin(bar_full + 8 * ab, use & 1);
+                fp_issue_layer(tacc, smem_u32(smem + L.off_a + (size_t)ab * L.a_bytes), s_w1, L.c_in, L.c1);
+                umma_commit(bar_empty + 8 * ab);
+                umma_commit(my_done);
             }
-            phase ^= 1;
-            tc_fence_before(); fence_proxy_async(); __syncthreads();
-            // ---- head layer 2: logits, no activation ----
-            if (tid == 0) fp_issue_layer(tmem, s_act, s_w4, L.h1, L.h2p, bar_mma);
-            phase ^= 1;
-            if (warp < 4) {
-                mbar_wait(bar_mma, phase ^ 1);
+            __syncwarp();
+            mbar_wait(my_done, phase); phase ^= 1;
+            tc_fence_after();
+            fp_epilogue_relu(lane_taddr, L.c1, b1, hbuf, row, nullptr, 0);
+            tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
+            // ---- layer 2 (FP output)
+            if (issuer) { fp_issue_layer(tacc, s_h, s_w2, L.c1, L.c2); umma_commit(my_done); }
+            __syncwarp();
+            mbar_wait(my_done, phase); phase ^= 1;
+            tc_fence_after();
+            fp_epilogue_relu(lane_taddr, L.c2, b2, hbuf, row, live ? a.out_feat + ((size_t)cloud * L.c2) * a.n + pt : nullptr, (size_t)a.n);
+            tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
+            if (L.h1) {
+                // ---- head layer 1
+                if (issuer) { fp_issue_layer(tacc, s_h, s_w3, L.c2, L.h1); umma_commit(my_done); }
+                __syncwarp();
+                mbar_wait(my_done, phase); phase ^= 1;
+                tc_fence_after();
+                fp_epilogue_relu(lane_taddr, L.h1, b3, hbuf, row, nullptr, 0);
+                tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
+                // ---- head layer 2: logits, no activation
+                if (issuer) { fp_issue_layer(tacc, s_h, s_w4, L.h1, L.h2p); umma_commit(my_done); }
+                __syncwarp();
+                mbar_wait(my_done, phase); phase ^= 1;
                 tc_fence_after();
                 float v[16];
                 tmem_ld16(lane_taddr, v);
@@ -271,8 +336,8 @@ fp_interp_mlp_kernel(const FpArgs a) {
                     for (int j = 0; j < 16; ++j)
                         if (j < L.h2) o[j] = v[j] + b4[j];
                 }
+                tc_fence_before(); group_bar(bar_id);            // every warp has drained D: the next tile's layer 1 may overwrite it
             }
-            tc_fence_before(); __syncthreads();
         }
     }
     tc_fence_before();
@@ -326,7 +391,7 @@ G4D_API int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int 
     if (b < 0 || n < 0 || m <= 0) return bad_arg("fp_interp_mlp: bad size");
     if (b == 0 || n == 0) return 0;
     if (!params_dev || !dist2 || !idx || !known_pm || !out_feat || (a.L.h1 && !out_head)) return bad_arg("fp_interp_mlp: null pointer");
-    if ((long long)b * m > 0xFFFFFFFEll) return bad_arg("fp_interp_mlp: b*m exceeds 32-bit point ids");
+    if ((long long)b * m * (d->c_in / 8) > 0xFFFFFFFEll) return bad_arg("fp_interp_mlp: b*m*c_in/8 exceeds 32-bit chunk ids");
     if (((uintptr_t)params_dev & 15) || ((uintptr_t)known_pm & 15)) return bad_arg("fp_interp_mlp: params/known_pm must be 16-byte aligned");
     a.n = n; a.m = m;
     a.total_rows = (long long)b * n;
@@ -338,12 +403,7 @@ G4D_API int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int 
     cudaError_t e = cudaFuncSetAttribute(fp_interp_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
     if (e != cudaSuccess) { set_error("fp_interp_mlp: shared memory opt-in (%u B): %s", a.L.total_smem, cudaGetErrorString(e)); return (int)e; }
     cudaFuncSetAttribute(fp_interp_mlp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    int occ = (int)((227u * 1024u) / (a.L.total_smem + 1024u));
-    const int tmem_limit = 512 / (int)a.L.tmem_cols;
-    if (occ > tmem_limit) occ = tmem_limit;
-    if (occ > 2) occ = 2;          // 128 registers x 256 threads
-    if (occ < 1) occ = 1;
-    long long grid = (long long)sm_count() * occ;
+    long long grid = sm_count();                                   // one persistent CTA per SM (all of its shared memory, half its TMEM)
     if (grid > a.ntiles) grid = a.ntiles;
     fp_interp_mlp_kernel<<<(unsigned)grid, FP_THREADS, a.L.total_smem, (cudaStream_t)stream>>>(a);
     return finish_launch("g4d fp_interp_mlp");

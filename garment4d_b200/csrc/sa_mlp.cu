@@ -139,44 +139,6 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
     }
 }
 
-// Shared-memory matrix descriptor split in halves: the high word (SBO = 128 B, version 1) is constant, the low word is
-// (address >> 4) | (LBO >> 4) << 16 and advances by a plain 32-bit add from one MMA to the next (the issuing lane is a
-// single thread: every dependent instruction on its path is latency, measured ~58 cycles per issued MMA before this).
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
-__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | lo; }
-
-// Wait used by roles that are far off the critical path (producers waiting for a free ring slot): poll, then sleep.
-// A tight try_wait loop in 8 idle warps would take most of the SM's issue slots away from the epilogue warps.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    for (;;) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(256);
-    }
-}
-
-// Spinning wait (no suspend-time hint) for the single MMA-issuing lane: it is the critical path of every hand-off.
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------------------
 

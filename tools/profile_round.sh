@@ -23,7 +23,7 @@ if [ "${SKIP_NCU:-0}" != 1 ]; then
   echo "ncu launches exit $?"
   # full sections for every kernel of libgarment4d_b200.so, one launch each at c3 sizes
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:'sa_mlp_max|fps_pruned|fps_kernel|ball_query_grid|query_and_group|fp_interp_mlp|lbs_|sgemm_acc|three_nn_grid|three_interpolate|grid_build|bias_relu' \
+      --kernel-name-base demangled -k regex:'g4d::' \
       -f -o $OUT/${TAG}_full python tools/ncu_once.py c3 > $OUT/${TAG}_full_run.log 2>&1
   echo "ncu full exit $?"
 fi
