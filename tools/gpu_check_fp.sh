@@ -5,10 +5,10 @@ set -u
 TAG="${1:-r01b}"
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 300 python -m pytest tests/test_sa_mlp_gpu.py tests/test_parity_gpu.py -x -q -m gpu -k "fp0 or fp_interp or bias_relu" > $OUT/${TAG}_fp_tests.log 2>&1
+timeout -k 10 300 python -m pytest tests/test_sa_mlp_gpu.py tests/test_parity_gpu.py -x -q -m gpu -k "fp0 or fp_interp or bias_relu" > $OUT/${TAG}_fp_tests.log 2>&1
 rc=$?; echo "fp tests exit $rc"; tail -15 $OUT/${TAG}_fp_tests.log
 if [ $rc -ne 0 ]; then exit $rc; fi
-timeout 240 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest "tests/test_sa_mlp_gpu.py::test_fused_fp0_head_vs_modules[1000]" -x -q -m gpu > $OUT/${TAG}_memcheck.log 2>&1
+timeout -k 10 240 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest "tests/test_sa_mlp_gpu.py::test_fused_fp0_head_vs_modules[1000]" -x -q -m gpu > $OUT/${TAG}_memcheck.log 2>&1
 echo "memcheck exit $?"; grep -E "ERROR SUMMARY|Invalid|passed|failed" $OUT/${TAG}_memcheck.log | tail -5
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 $OUT/${TAG}_pytest_gpu.log
 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
