@@ -89,6 +89,12 @@ struct FpArgs {
     float* out_head;             // (b, n, h2) or null
 };
 
+// one 256-bit read-only load (LDG.E.256, sm_100+): 32 bytes per lane, p 32-byte aligned
+__device__ __forceinline__ void ldg256(const uint4* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}
+
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
     const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
@@ -99,10 +105,13 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 __device__ __forceinline__ void fp_epilogue_relu(uint32_t lane_taddr, int ncols, const float* bias, unsigned char* hbuf, int row,
                                                  float* gout /* channel 0 of this row's point, or null */, size_t gstride) {
     for (int c0 = 0; c0 < ncols; c0 += 16) {
-        float v[16];
+        float v[16], bv[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)                             // 4 broadcast LDS.128 instead of 16 LDS.32: the LSU data pipe is the scarce unit here
+            *reinterpret_cast<float4*>(bv + 4 * i) = *reinterpret_cast<const float4*>(bias + c0 + 4 * i);
         tmem_ld16(lane_taddr + c0, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bias[c0 + i], 0.f);
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bv[i], 0.f);
         if (gout) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) gout[(size_t)(c0 + i) * gstride] = v[i];     // lanes = consecutive points: coalesced
@@ -217,8 +226,11 @@ fp_interp_mlp_kernel(const FpArgs a) {
             const uint32_t use = (uint32_t)(i / NA);
             mbar_wait(bar_empty + 8 * ab, (use & 1) ^ 1);       // freed by the commit of layer 1 of tile i - NA (first lap passes)
             uint4* dst = reinterpret_cast<uint4*>(smem + L.off_a + (size_t)ab * L.a_bytes);
-            // ---- gather + interpolate: warp pw owns rows 32pw..32pw+31 in two rounds of 16 rows = 2 groups of 8 rows;
-            //      4 chunks per lane per group; the 24 loads of a round are issued before their first use
+            // ---- gather + interpolate: warp pw owns rows 32pw..32pw+31 in two rounds of 16 rows = 2 groups of 8 rows.
+            //      Lane (rl, cl) loads 32 bytes (two 8-channel chunks) per tap with ONE 256-bit load, so that a warp-wide load
+            //      covers 8 rows x 128 B = 8 full cache lines: the L1TEX data pipe (one wavefront per line touched) is the
+            //      bottleneck of this kernel -- with 16-byte loads over 8 rows x 64 B the same bytes cost twice the wavefronts.
+            //      The 12 loads of a round (2 row groups x 3 taps x 2 column blocks = 12 KB per warp) are issued before their first use.
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 uint32_t q[2][3];                                // chunk index of the tap's row start (point id * chunks per row)
@@ -236,37 +248,39 @@ fp_interp_mlp_kernel(const FpArgs a) {
                     }
                 }
 #pragma unroll 1
-                for (int cb = cl; cb < nchunk; cb += 16) {
-                    uint4 ld[2][3][4];
+                for (int cb = 2 * cl; cb < nchunk; cb += 16) {    // this lane's chunk pair of each 16-chunk column block pair
+                    uint4 ld[2][3][2][2];                         // [row group][tap][column block][chunk of the pair]
 #pragma unroll
                     for (int rg = 0; rg < 2; ++rg)
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int c = cb + 4 * u;
+                        for (int u = 0; u < 2; ++u) {
+                            const int c = cb + 8 * u;
 #pragma unroll
                             for (int k = 0; k < 3; ++k) {
-                                ld[rg][k][u] = make_uint4(0, 0, 0, 0);
-                                if (c < nchunk && valid[rg]) ld[rg][k][u] = __ldg(kp + (q[rg][k] + (uint32_t)c));
+                                ld[rg][k][u][0] = ld[rg][k][u][1] = make_uint4(0, 0, 0, 0);
+                                if (c < nchunk && valid[rg]) ldg256(kp + (q[rg][k] + (uint32_t)c), ld[rg][k][u][0], ld[rg][k][u][1]);
                             }
                         }
 #pragma unroll
                     for (int rg = 0; rg < 2; ++rg) {
                         const int row = pw * 32 + h * 16 + rg * 8 + rl;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int c = cb + 4 * u;
-                            if (c < nchunk) {
-                                float f0[8], f1[8], f2[8], r[8];
-                                unpack8(ld[rg][0][u], f0); unpack8(ld[rg][1][u], f1); unpack8(ld[rg][2][u], f2);
+                        for (int u = 0; u < 2; ++u)
 #pragma unroll
-                                for (int e = 0; e < 8; ++e)     // interpolate_gpu.cu:96 in the reference build's order
-                                    r[e] = __fmaf_rn(wt[rg][2], f2[e], __fmaf_rn(wt[rg][0], f0[e], __fmul_rn(wt[rg][1], f1[e])));
-                                uint4 o = make_uint4(0, 0, 0, 0);
-                                if (valid[rg])
-                                    o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
-                                dst[(size_t)c * FP_TILE + row] = o;
+                            for (int e2 = 0; e2 < 2; ++e2) {
+                                const int c = cb + 8 * u + e2;
+                                if (c < nchunk) {
+                                    float f0[8], f1[8], f2[8], r[8];
+                                    unpack8(ld[rg][0][u][e2], f0); unpack8(ld[rg][1][u][e2], f1); unpack8(ld[rg][2][u][e2], f2);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e)     // interpolate_gpu.cu:96 in the reference build's order
+                                        r[e] = __fmaf_rn(wt[rg][2], f2[e], __fmaf_rn(wt[rg][0], f0[e], __fmul_rn(wt[rg][1], f1[e])));
+                                    uint4 o = make_uint4(0, 0, 0, 0);
+                                    if (valid[rg])
+                                        o = make_uint4(pack_f16x2(r[0], r[1]), pack_f16x2(r[2], r[3]), pack_f16x2(r[4], r[5]), pack_f16x2(r[6], r[7]));
+                                    dst[(size_t)c * FP_TILE + row] = o;
+                                }
                             }
-                        }
                     }
                 }
             }
@@ -392,7 +406,7 @@ G4D_API int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int 
     if (b == 0 || n == 0) return 0;
     if (!params_dev || !dist2 || !idx || !known_pm || !out_feat || (a.L.h1 && !out_head)) return bad_arg("fp_interp_mlp: null pointer");
     if ((long long)b * m * (d->c_in / 8) > 0xFFFFFFFEll) return bad_arg("fp_interp_mlp: b*m*c_in/8 exceeds 32-bit chunk ids");
-    if (((uintptr_t)params_dev & 15) || ((uintptr_t)known_pm & 15)) return bad_arg("fp_interp_mlp: params/known_pm must be 16-byte aligned");
+    if (((uintptr_t)params_dev & 15) || ((uintptr_t)known_pm & 31)) return bad_arg("fp_interp_mlp: params must be 16-byte, known_pm 32-byte aligned");
     a.n = n; a.m = m;
     a.total_rows = (long long)b * n;
     const long long nt = (a.total_rows + FP_TILE - 1) / FP_TILE;

@@ -13,6 +13,7 @@ names (``groupers``, ``mlps.{i}.layer{j}.conv.weight`` ...), same ``forward`` si
   each operator on the B200 kernels (fused QueryAndGroup, then torch conv/bn/relu and pooling).
 """
 import ctypes
+import os
 from typing import List
 
 import torch
@@ -22,6 +23,10 @@ import torch.nn.functional as F
 from .. import _lib
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
+
+
+# G4D_FP_FUSED_CONV=1: FP-module 1x1 convolutions through cuDNN's fused conv+bias+ReLU entry (one pass less per layer)
+_FUSED_CONV = os.environ.get("G4D_FP_FUSED_CONV", "0") == "1"
 
 
 def _as_point_major_half(features: torch.Tensor) -> torch.Tensor:
@@ -240,8 +245,12 @@ class PointnetFPModule(nn.Module):
             # next (finer) level's fused kernel gathers from (attached as ``_g4d_pm``, like the SA modules do)
             y = new_features
             for li, (w, b) in enumerate(folded):
-                y = F.conv2d(y.unsqueeze(-1), w).squeeze(-1)
                 last = li == len(folded) - 1
+                if _FUSED_CONV and not (last and self.emit_point_major):
+                    # library convolution with the bias + ReLU epilogue fused (cudnnConvolutionBiasActivationForward)
+                    y = torch.cudnn_convolution_relu(y.unsqueeze(-1), w, b, [1, 1], [0, 0], [1, 1], 1).squeeze(-1)
+                    continue
+                y = F.conv2d(y.unsqueeze(-1), w).squeeze(-1)
                 if last and self.emit_point_major and y.is_contiguous() and y.shape[0] <= 65535:
                     pm = torch.empty(y.shape[0], y.shape[2], y.shape[1], dtype=torch.float16, device=y.device)
                     rc = L.g4d_bias_relu_pm(y.shape[0], y.shape[1], y.shape[2], _lib.ptr(y), _lib.ptr(b), 1, _lib.ptr(pm), _lib.stream_ptr())
