@@ -179,9 +179,16 @@ G4D_API int g4d_bias_relu_inplace(int b, int c, long long n, float* y, const flo
 // equal the torch tensors bit for bit), then the thread walks a slab of output channels; the skip channels are a
 // coalesced copy.  Same FMUL/FFMA order as three_interpolate_kernel.
 namespace g4d {
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(__half* p, float v) { *p = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+
+// out element (bi, ci, pt) lives at ci * out_cs + bi * out_bs + pt: (b, c, n) fp32 for the reference layout, or (c, b, n) fp16 so
+// that the following 1x1 convolutions are ONE (Cout x Cin) . (Cin x b*n) GEMM over the whole batch.
+template <typename OutT>
 __global__ void __launch_bounds__(256)
 fp_interp_concat_kernel(int c2, int c1, int m, int n, const float* __restrict__ dist2, const int* __restrict__ idx,
-                        const float* __restrict__ known_feats, const float* __restrict__ skip, float* __restrict__ out) {
+                        const float* __restrict__ known_feats, const float* __restrict__ skip, OutT* __restrict__ out,
+                        long long out_cs, long long out_bs) {
     const size_t bi = blockIdx.z;
     const int pt = blockIdx.x * blockDim.x + threadIdx.x;
     if (pt >= n) return;
@@ -198,6 +205,7 @@ fp_interp_concat_kernel(int c2, int c1, int m, int n, const float* __restrict__ 
         const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
         w0 = __fdiv_rn(r0, norm); w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm);
     }
+    OutT* o = out + bi * out_bs + pt;
     for (int ci = blockIdx.y; ci < ctot; ci += gridDim.y) {
         float v;
         if (ci < c2) {
@@ -206,7 +214,59 @@ fp_interp_concat_kernel(int c2, int c1, int m, int n, const float* __restrict__ 
         } else {
             v = __ldg(skip + (bi * c1 + (ci - c2)) * (size_t)n + pt);
         }
-        out[(bi * ctot + ci) * (size_t)n + pt] = v;
+        store_out(o + ci * out_cs, v);
+    }
+}
+
+// y (c, len) fp16: y[ch, :] = act(y[ch, :] + bias[ch]) in place, 8 halves per thread (len % 8 == 0)
+__global__ void __launch_bounds__(256)
+bias_relu_h_kernel(long long len8, int relu, uint4* __restrict__ y, const float* __restrict__ bias) {
+    const float bv = __ldg(bias + blockIdx.y);
+    uint4* p = y + (size_t)blockIdx.y * len8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len8; i += (long long)gridDim.x * blockDim.x) {
+        uint4 v = p[i];
+        __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 f = __half22float2(h[k]);
+            f.x += bv; f.y += bv;
+            if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+            h[k] = __floats2half2_rn(fminf(f.x, 65504.f), fminf(f.y, 65504.f));
+        }
+        p[i] = v;
+    }
+}
+
+__device__ __forceinline__ float load_in(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_in(const __half* p) { return __half2float(*p); }
+
+// Last layer of the batched-GEMM route: yin (c, b, n) (fp32 or fp16, pre-activation) -> out_cm (b, c, n) fp32 = act(yin + bias)
+// and, optionally, the same values fp16 point-major out_pm (b, n, c).  32 x 32 (channel x point) tiles through shared memory.
+template <typename InT>
+__global__ void __launch_bounds__(256)
+bias_relu_unpack_kernel(int b, int c, int n, int relu, const InT* __restrict__ yin, const float* __restrict__ bias,
+                        float* __restrict__ out_cm, __half* __restrict__ out_pm) {
+    __shared__ float tile[32][33];
+    const size_t bi = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ch = c0 + ty + 8 * r, pt = p0 + tx;
+        float v = 0.f;
+        if (ch < c && pt < n) {
+            v = load_in(yin + ((size_t)ch * b + bi) * n + pt) + __ldg(bias + ch);
+            if (relu) v = fmaxf(v, 0.f);
+            out_cm[(bi * c + ch) * (size_t)n + pt] = v;
+        }
+        tile[ty + 8 * r][tx] = v;
+    }
+    if (!out_pm) return;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int pt = p0 + ty + 8 * r, ch = c0 + tx;
+        if (ch < c && pt < n) out_pm[(bi * n + pt) * (size_t)c + ch] = __float2half_rn(fminf(tile[tx][ty + 8 * r], 65504.f));
     }
 }
 
@@ -240,16 +300,59 @@ bias_relu_pm_kernel(int c, int n, int relu, float* __restrict__ y, const float* 
 }
 }  // namespace g4d
 
-G4D_API int g4d_fp_interp_concat(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const float* known_feats,
-                                 const float* skip, float* out, void* stream) {
+static int fp_interp_concat_check(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const float* known_feats,
+                                  const float* skip, const void* out) {
     if (b < 0 || c2 < 0 || c1 < 0 || n < 0 || m < 0) return bad_arg("fp_interp_concat: negative size");
-    if (b == 0 || n == 0 || c2 + c1 == 0) return 0;
+    if (b == 0 || n == 0 || c2 + c1 == 0) return -1;
     if (!out || (c2 > 0 && (!dist2 || !idx || !known_feats || m == 0)) || (c1 > 0 && !skip)) return bad_arg("fp_interp_concat: null pointer");
     if (b > 65535) return bad_arg("fp_interp_concat: b > 65535");
+    return 0;
+}
+
+G4D_API int g4d_fp_interp_concat(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const float* known_feats,
+                                 const float* skip, float* out, void* stream) {
+    const int rc = fp_interp_concat_check(b, c2, c1, m, n, dist2, idx, known_feats, skip, out);
+    if (rc) return rc < 0 ? 0 : rc;
     const int ctot = c2 + c1;
     dim3 grid((n + 255) / 256, ctot < 16 ? ctot : 16, b);
-    fp_interp_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c2, c1, m, n, dist2, idx, known_feats, skip, out);
+    fp_interp_concat_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(c2, c1, m, n, dist2, idx, known_feats, skip, out,
+                                                                           (long long)n, (long long)ctot * n);
     return finish_launch("g4d fp_interp_concat");
+}
+
+G4D_API int g4d_fp_interp_concat_cbn_h(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const float* known_feats,
+                                       const float* skip, void* out_h, void* stream) {
+    const int rc = fp_interp_concat_check(b, c2, c1, m, n, dist2, idx, known_feats, skip, out_h);
+    if (rc) return rc < 0 ? 0 : rc;
+    const int ctot = c2 + c1;
+    dim3 grid((n + 255) / 256, ctot < 16 ? ctot : 16, b);
+    fp_interp_concat_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(c2, c1, m, n, dist2, idx, known_feats, skip, (__half*)out_h,
+                                                                            (long long)b * n, (long long)n);
+    return finish_launch("g4d fp_interp_concat_cbn_h");
+}
+
+G4D_API int g4d_bias_relu_h(int c, long long len, void* y_h, const float* bias, int relu, void* stream) {
+    if (c < 0 || len < 0) return bad_arg("bias_relu_h: negative size");
+    if (c == 0 || len == 0) return 0;
+    if (!y_h || !bias) return bad_arg("bias_relu_h: null pointer");
+    if (len % 8 || ((uintptr_t)y_h & 15)) return bad_arg("bias_relu_h: row length must be a multiple of 8 and y 16-byte aligned");
+    if (c > 65535) return bad_arg("bias_relu_h: c > 65535");
+    const long long len8 = len / 8;
+    dim3 grid((unsigned)((len8 + 255) / 256 > 256 ? 256 : (len8 + 255) / 256), (unsigned)c);
+    bias_relu_h_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(len8, relu, (uint4*)y_h, bias);
+    return finish_launch("g4d bias_relu_h");
+}
+
+G4D_API int g4d_bias_relu_unpack(int b, int c, int n, const void* yin_cbn, int in_half, const float* bias, int relu, float* out_cm,
+                                 void* out_pm, void* stream) {
+    if (b < 0 || c < 0 || n < 0) return bad_arg("bias_relu_unpack: negative size");
+    if (b == 0 || c == 0 || n == 0) return 0;
+    if (!yin_cbn || !bias || !out_cm) return bad_arg("bias_relu_unpack: null pointer");
+    if (b > 65535 || (c + 31) / 32 > 65535) return bad_arg("bias_relu_unpack: b or c/32 > 65535");
+    dim3 grid((n + 31) / 32, (c + 31) / 32, b);
+    if (in_half) bias_relu_unpack_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(b, c, n, relu, (const __half*)yin_cbn, bias, out_cm, (__half*)out_pm);
+    else bias_relu_unpack_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(b, c, n, relu, (const float*)yin_cbn, bias, out_cm, (__half*)out_pm);
+    return finish_launch("g4d bias_relu_unpack");
 }
 
 G4D_API int g4d_bias_relu_pm(int b, int c, int n, float* y, const float* bias, int relu, void* out_pm, void* stream) {

@@ -25,8 +25,9 @@ from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
 
-# G4D_FP_FUSED_CONV=1: FP-module 1x1 convolutions through cuDNN's fused conv+bias+ReLU entry (one pass less per layer)
-_FUSED_CONV = os.environ.get("G4D_FP_FUSED_CONV", "0") == "1"
+# Feature-propagation MLPs in eval mode: "half" = one fp16 library GEMM per layer over the whole batch (default),
+# "conv" = per-cloud fp32/TF32 library convolution.  Both with our prologue / bias+ReLU epilogue kernels.
+_FP_GEMM = os.environ.get("G4D_FP_GEMM", "half")
 
 
 def _as_point_major_half(features: torch.Tensor) -> torch.Tensor:
@@ -213,16 +214,42 @@ class PointnetFPModule(nn.Module):
         L = _lib.lib() if folded is not None else None
         if (folded is not None and known is not None and known_feats.dtype == torch.float32
                 and (unknow_feats is None or unknow_feats.dtype == torch.float32)):
-            # eval route: three_nn -> ONE kernel for weights + three_interpolate + cat (g4d_fp_interp_concat)
+            # eval route: three_nn -> ONE kernel for weights + three_interpolate + cat
             unknown, known, known_feats = unknown.contiguous(), known.contiguous(), known_feats.contiguous()
             B, n, _ = unknown.shape
             m, c2 = known.shape[1], known_feats.shape[1]
             c1 = 0 if unknow_feats is None else unknow_feats.shape[1]
             skip = None if unknow_feats is None else unknow_feats.contiguous()
-            dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
-            idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
+            dev = unknown.device
+            dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+            idx = torch.empty(B, n, 3, dtype=torch.int32, device=dev)
             pointnet2_utils.three_nn_raw(unknown, known, dist2, idx)
-            new_features = torch.empty(B, c2 + c1, n, dtype=torch.float32, device=unknown.device)
+            if _FP_GEMM == "half" and folded["half"] is not None and (B * n) % 8 == 0 and B <= 65535:
+                # The module's 1x1 convolutions as ONE library GEMM per layer over the whole batch: the concatenated input is
+                # written fp16 in (C, B*n) layout, hidden layers stay fp16 (fp32 accumulation; same 11-bit operand precision
+                # as the TF32 convolutions torch runs by default), bias+ReLU passes are ours, the last layer's GEMM returns
+                # fp32 and its epilogue writes the reference layout (B, C, n) (+ the fp16 point-major copy for the next level).
+                x = torch.empty(c2 + c1, B * n, dtype=torch.float16, device=dev)
+                rc = L.g4d_fp_interp_concat_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(known_feats), _lib.ptr(skip),
+                                                  _lib.ptr(x), _lib.stream_ptr())
+                _lib.check(rc, "g4d_fp_interp_concat_cbn_h")
+                layers = folded["half"]
+                for li, (w16, b) in enumerate(layers):
+                    if li < len(layers) - 1:
+                        x = torch.mm(w16, x)
+                        rc = L.g4d_bias_relu_h(w16.shape[0], B * n, _lib.ptr(x), _lib.ptr(b), 1, _lib.stream_ptr())
+                        _lib.check(rc, "g4d_bias_relu_h")
+                    else:
+                        y = torch.mm(w16, x, out_dtype=torch.float32)
+                        out = torch.empty(B, w16.shape[0], n, dtype=torch.float32, device=dev)
+                        pm = torch.empty(B, n, w16.shape[0], dtype=torch.float16, device=dev) if self.emit_point_major else None
+                        rc = L.g4d_bias_relu_unpack(B, w16.shape[0], n, _lib.ptr(y), 0, _lib.ptr(b), 1, _lib.ptr(out), _lib.ptr(pm),
+                                                    _lib.stream_ptr())
+                        _lib.check(rc, "g4d_bias_relu_unpack")
+                        if pm is not None:
+                            out._g4d_pm = pm
+                return out
+            new_features = torch.empty(B, c2 + c1, n, dtype=torch.float32, device=dev)
             rc = L.g4d_fp_interp_concat(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(known_feats), _lib.ptr(skip),
                                         _lib.ptr(new_features), _lib.stream_ptr())
             _lib.check(rc, "g4d_fp_interp_concat")
@@ -240,16 +267,13 @@ class PointnetFPModule(nn.Module):
             else:
                 new_features = interpolated_feats
         if folded is not None:
-            # eval mode, no autograd: BatchNorm folded into the 1x1 convolutions -> library GEMM (1x1 conv, no bias) + ONE
-            # in-place bias+ReLU pass of ours per layer; the last layer's pass also emits the fp16 point-major copy that the
-            # next (finer) level's fused kernel gathers from (attached as ``_g4d_pm``, like the SA modules do)
+            # eval mode, no autograd, per-cloud route (G4D_FP_GEMM=conv): BatchNorm folded into the 1x1 convolutions -> library
+            # convolution (no bias) + ONE in-place bias+ReLU pass of ours per layer; the last layer's pass also emits the fp16
+            # point-major copy that the next (finer) level's fused kernel gathers from (attached as ``_g4d_pm``)
             y = new_features
-            for li, (w, b) in enumerate(folded):
-                last = li == len(folded) - 1
-                if _FUSED_CONV and not (last and self.emit_point_major):
-                    # library convolution with the bias + ReLU epilogue fused (cudnnConvolutionBiasActivationForward)
-                    y = torch.cudnn_convolution_relu(y.unsqueeze(-1), w, b, [1, 1], [0, 0], [1, 1], 1).squeeze(-1)
-                    continue
+            layers = folded["conv"]
+            for li, (w, b) in enumerate(layers):
+                last = li == len(layers) - 1
                 y = F.conv2d(y.unsqueeze(-1), w).squeeze(-1)
                 if last and self.emit_point_major and y.is_contiguous() and y.shape[0] <= 65535:
                     pm = torch.empty(y.shape[0], y.shape[2], y.shape[1], dtype=torch.float16, device=y.device)
@@ -274,6 +298,11 @@ class PointnetFPModule(nn.Module):
         hit = getattr(self, "_fold_cache", None)
         if hit is None or hit[0] != ver:
             f = pt_utils.fold_shared_mlp(self.mlp)
-            hit = (ver, None if f is None else [(w[:, :, None, None].contiguous(), b) for w, b in f])
+            hit = (ver, None)
+            if f is not None:
+                half = [(w.to(torch.float16).contiguous(), b) for w, b in f]
+                if not all(bool(torch.isfinite(w).all()) for w, _ in half):     # folded weight outside the fp16 range: keep fp32
+                    half = None
+                hit = (ver, {"conv": [(w[:, :, None, None].contiguous(), b) for w, b in f], "half": half})
             self._fold_cache = hit
         return hit[1]

@@ -170,6 +170,17 @@ int g4d_bias_relu_inplace(int b, int c, long long n, float* y, const float* bias
 int g4d_fp_interp_concat(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const float* known_feats,
                          const float* skip, float* out, void* stream);
 
+/* The same with the result as fp16 in (c, b, n) layout, out_h[(ci * b + bi) * n + pt]: the operand of ONE batched
+ * (Cout x Cin) . (Cin x b*n) GEMM for the module's 1x1 convolutions (pointnet2_modules.py:153-154). */
+int g4d_fp_interp_concat_cbn_h(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const float* known_feats,
+                               const float* skip, void* out_h, void* stream);
+/* y (c, len) fp16, in place: y[ch,:] = max(y[ch,:] + bias[ch], 0) (relu = 0: bias only); len % 8 == 0 */
+int g4d_bias_relu_h(int c, long long len, void* y_h, const float* bias, int relu, void* stream);
+/* epilogue of the last layer of that route: yin (c, b, n) pre-activations (fp32, or fp16 when in_half) ->
+ * out_cm (b, c, n) fp32 = act(yin + bias) and, when out_pm != NULL, the same values fp16 point-major (b, n, c) */
+int g4d_bias_relu_unpack(int b, int c, int n, const void* yin_cbn, int in_half, const float* bias, int relu, float* out_cm,
+                         void* out_pm, void* stream);
+
 /* g4d_bias_relu_inplace that ALSO writes the activated values as fp16 point-major out_pm (b,n,c): the gather layout of
  * g4d_fp_interp_mlp / g4d_sa_mlp_max (replaces transpose(1,2).to(half).contiguous() on the next level's input). */
 int g4d_bias_relu_pm(int b, int c, int n, float* y, const float* bias, int relu, void* out_pm, void* stream);

@@ -289,3 +289,48 @@ def test_bias_relu_pm(cuda):
         want = torch.relu(y0 + b[None, :, None])
         assert torch.equal(y, want)
         assert torch.equal(pm, want.transpose(1, 2).to(torch.float16).contiguous())
+
+
+def test_fp_batched_gemm_route_entry_points(cuda):
+    """g4d_fp_interp_concat_cbn_h / g4d_bias_relu_h / g4d_bias_relu_unpack against the fp32 entry points and torch."""
+    from garment4d_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.RandomState(61)
+    B, n, m, c2, c1 = 3, 256, 64, 40, 24
+    unknown = clouds(61, B, n, "body", dup_frac=0.02)
+    u, k = _t(unknown, cuda), _t(unknown[:, :m].copy(), cuda)
+    kf = _t(rs.randn(B, c2, m).astype(np.float32), cuda)
+    skip = _t(rs.randn(B, c1, n).astype(np.float32), cuda)
+    dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=cuda)
+    idx = torch.empty(B, n, 3, dtype=torch.int32, device=cuda)
+    pu.three_nn_raw(u, k, dist2, idx)
+    ref = torch.empty(B, c2 + c1, n, dtype=torch.float32, device=cuda)
+    _lib.check(L.g4d_fp_interp_concat(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kf), _lib.ptr(skip), _lib.ptr(ref),
+                                      _lib.stream_ptr()), "g4d_fp_interp_concat")
+    xh = torch.zeros(c2 + c1, B * n, dtype=torch.float16, device=cuda)
+    _lib.check(L.g4d_fp_interp_concat_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kf), _lib.ptr(skip), _lib.ptr(xh),
+                                            _lib.stream_ptr()), "g4d_fp_interp_concat_cbn_h")
+    assert torch.equal(xh.view(c2 + c1, B, n), ref.permute(1, 0, 2).to(torch.float16))
+    # bias + ReLU on (c, len) fp16
+    C, ln = 37, 8 * 123
+    y0 = _t((rs.randn(C, ln) * 3).astype(np.float16), cuda)
+    b = _t(rs.randn(C).astype(np.float32), cuda)
+    y = y0.clone()
+    _lib.check(L.g4d_bias_relu_h(C, ln, _lib.ptr(y), _lib.ptr(b), 1, _lib.stream_ptr()), "g4d_bias_relu_h")
+    assert torch.equal(y, torch.relu(y0.float() + b[:, None]).to(torch.float16))
+    # last-layer epilogue: (c, b, n) -> (b, c, n) fp32 (+ fp16 point-major)
+    for in_half in (0, 1):
+        for (Bq, Cq, nq) in [(2, 128, 1024), (3, 50, 77)]:
+            yin = _t((rs.randn(Cq, Bq, nq) * 3).astype(np.float16 if in_half else np.float32), cuda)
+            bq = _t(rs.randn(Cq).astype(np.float32), cuda)
+            out = torch.zeros(Bq, Cq, nq, dtype=torch.float32, device=cuda)
+            pm = torch.zeros(Bq, nq, Cq, dtype=torch.float16, device=cuda)
+            _lib.check(L.g4d_bias_relu_unpack(Bq, Cq, nq, _lib.ptr(yin), in_half, _lib.ptr(bq), 1, _lib.ptr(out), _lib.ptr(pm),
+                                              _lib.stream_ptr()), "g4d_bias_relu_unpack")
+            want = torch.relu(yin.float() + bq[:, None, None]).permute(1, 0, 2).contiguous()
+            assert torch.equal(out, want)
+            assert torch.equal(pm, want.transpose(1, 2).to(torch.float16).contiguous())
+            out2 = torch.zeros_like(out)
+            _lib.check(L.g4d_bias_relu_unpack(Bq, Cq, nq, _lib.ptr(yin), in_half, _lib.ptr(bq), 1, _lib.ptr(out2), None,
+                                              _lib.stream_ptr()), "g4d_bias_relu_unpack")
+            assert torch.equal(out2, want)

@@ -124,3 +124,37 @@ def test_fused_fp0_head_vs_modules(cuda, N):
     # 7 chained fp16-operand layers (3 SA + 2 FP + 2 head) end to end, FP1/FP2 through TF32 cuDNN: 5e-3 of the range
     _close(lf[0], lf_ref[0], tol=5e-3)
     _close(sem, sem_ref, tol=5e-3)
+
+
+@pytest.mark.parametrize("spec", [(1024, 256, 256, 96, [352, 256, 128]), (256, 64, 384, 192, [576, 512, 256]), (300, 41, 16, 0, [16, 24])],
+                         ids=lambda s: f"n{s[0]}m{s[1]}")
+def test_fp_module_eval_routes_vs_operator_sequence(cuda, spec):
+    """PointnetFPModule in eval mode (fused prologue + batched fp16 GEMMs, and the per-cloud conv route) against the
+    reference's operator sequence in true fp32 (training-style path of the same module under no_grad is not available:
+    run the module with autograd enabled so that it takes the operator route, BN in eval mode)."""
+    from garment4d_b200.pointnet2 import pointnet2_modules as pm
+    n, m, c2, c1, mlp = spec
+    torch.manual_seed(5)
+    mod = pm.PointnetFPModule(mlp=list(mlp), bn=True)
+    _randomise_bn(mod, 6)
+    mod = mod.to(cuda).eval()
+    B = 3
+    unknown = torch.from_numpy(clouds(12, B, n, "body")).to(cuda)
+    known = unknown[:, :m].contiguous()
+    kf = torch.randn(B, c2, m, device=cuda)
+    skip = torch.randn(B, c1, n, device=cuda) if c1 else None
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = mod(unknown, known, skip, kf.clone().requires_grad_(True)).detach()      # operator route (autograd on)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    with torch.no_grad():
+        for route in ("half", "conv"):
+            prev, pm._FP_GEMM = pm._FP_GEMM, route
+            try:
+                out = mod(unknown, known, skip, kf)
+            finally:
+                pm._FP_GEMM = prev
+            assert out.shape == ref.shape and out.dtype == torch.float32
+            _close(out, ref, tol=4e-3)
