@@ -22,6 +22,7 @@
 //   Only the FP output (channel-major fp32, returned by the encoder as l_features[0]) and the logits (point-major)
 //   are written to HBM.  (The first version ran gather and layers back to back in one 256-thread CTA with block-wide
 //   barriers: 31 % of its warp samples waited on the gather, 31 % at barriers -- profiles/r01_ncu_summary.md.)
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -68,6 +69,7 @@ static bool fp_layout(const g4d_fp_desc* d, FpLayout* L, const char** why) {
     if (L->off_a + 2 * L->a_bytes > budget) { *why = "fp: shared memory footprint exceeds 227 KB"; return false; }
     uint32_t na = (budget - L->off_a) / L->a_bytes;
     L->na = na > (uint32_t)FP_MAX_A ? (uint32_t)FP_MAX_A : na;
+    if (const char* e = getenv("G4D_FP_NA")) { const int v = atoi(e); if (v >= 2 && (uint32_t)v <= L->na) L->na = (uint32_t)v; }   // tuning knob
     L->total_smem = L->off_a + L->na * L->a_bytes;
     uint32_t p2 = 32;
     while (p2 < (uint32_t)hmax || p2 < (uint32_t)L->h2p) p2 <<= 1;
@@ -87,6 +89,7 @@ struct FpArgs {
     const unsigned char* params;
     float* out_feat;             // (b, c2, n) channel-major fp32
     float* out_head;             // (b, n, h2) or null
+    long long* dbg;              // optional cycle counters of CTA 0 (g4d_debug_fp_counters)
 };
 
 // one 256-bit read-only load (LDG.E.256, sm_100+): 32 bytes per lane, p 32-byte aligned
@@ -140,8 +143,15 @@ __device__ __forceinline__ void fp_issue_layer(uint32_t tmem, uint32_t s_act, ui
     }
 }
 
-__device__ __forceinline__ void group_bar(int id) {          // the 128 threads of one consumer / producer group
-    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+// Barrier of the 128 threads of one consumer / producer group.  Immediate barrier ids on purpose: with a register operand
+// ptxas reserves all 16 hardware barriers of the CTA (and Nsight Compute could not replay the kernel).
+__device__ __forceinline__ void group_bar(int id) {
+    switch (id) {
+        case 1: asm volatile("bar.sync 1, 128;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
+        case 3: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+    }
 }
 
 __global__ void __launch_bounds__(FP_THREADS, 1)
@@ -193,6 +203,8 @@ fp_interp_mlp_kernel(const FpArgs a) {
             d0 = __ldg(dp); d1 = __ldg(dp + 1); d2v = __ldg(dp + 2); j0 = __ldg(ip); j1 = __ldg(ip + 1); j2 = __ldg(ip + 2);
         }
         int buf = 0;
+        const bool dbgp = a.dbg && blockIdx.x == 0 && pg == 0 && pw == 0 && lane == 0;
+        long long t_wait_empty = 0, t_loop0 = dbgp ? clock64() : 0;
         for (int i = pg; i < nseq; i += FP_PG, buf ^= 1) {
             const long long R = Rn;
             const bool live = R < a.total_rows;
@@ -224,7 +236,9 @@ fp_interp_mlp_kernel(const FpArgs a) {
             // ---- A buffer of this tile
             const int ab = i % NA;
             const uint32_t use = (uint32_t)(i / NA);
+            const long long tw0 = dbgp ? clock64() : 0;
             mbar_wait(bar_empty + 8 * ab, (use & 1) ^ 1);       // freed by the commit of layer 1 of tile i - NA (first lap passes)
+            if (dbgp) t_wait_empty += clock64() - tw0;
             uint4* dst = reinterpret_cast<uint4*>(smem + L.off_a + (size_t)ab * L.a_bytes);
             // ---- gather + interpolate: warp pw owns rows 32pw..32pw+31 in two rounds of 16 rows = 2 groups of 8 rows.
             //      Lane (rl, cl) loads 32 bytes (two 8-channel chunks) per tap with ONE 256-bit load, so that a warp-wide load
@@ -288,6 +302,7 @@ fp_interp_mlp_kernel(const FpArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * ab);
         }
+        if (dbgp) { a.dbg[0] = t_wait_empty; a.dbg[1] = clock64() - t_loop0; }
     } else {
         // =========================== CONSUMERS ==================================================================
         const int cg = warp >> 2;                                // consumer group; its warps own TMEM lane quadrants warp & 3
@@ -303,6 +318,8 @@ fp_interp_mlp_kernel(const FpArgs a) {
         const int bar_id = 1 + cg;
         uint32_t phase = 0;
         mbar_wait(bar_w, 0);                                     // weights + biases resident
+        const bool dbgc = a.dbg && blockIdx.x == 0 && cg == 0 && issuer;
+        long long t_wait_full = 0, t_wait_done = 0, t_loop0 = dbgc ? clock64() : 0;
         for (int i = cg; i < nseq; i += FP_CG) {
             const long long R = ((long long)blockIdx.x + (long long)i * gridDim.x) * FP_TILE + row;
             const bool live = R < a.total_rows;
@@ -312,13 +329,17 @@ fp_interp_mlp_kernel(const FpArgs a) {
             const uint32_t use = (uint32_t)(i / NA);
             // ---- layer 1: A buffer -> D ; its commit releases the A buffer to the producers
             if (issuer) {
+                const long long tw0 = dbgc ? clock64() : 0;
                 mbar_wait_spin(bar_full + 8 * ab, use & 1);
+                if (dbgc) t_wait_full += clock64() - tw0;
                 fp_issue_layer(tacc, smem_u32(smem + L.off_a + (size_t)ab * L.a_bytes), s_w1, L.c_in, L.c1);
                 umma_commit(bar_empty + 8 * ab);
                 umma_commit(my_done);
             }
             __syncwarp();
-            mbar_wait(my_done, phase); phase ^= 1;
+            { const long long tw0 = dbgc ? clock64() : 0;
+              mbar_wait(my_done, phase); phase ^= 1;
+              if (dbgc) t_wait_done += clock64() - tw0; }
             tc_fence_after();
             fp_epilogue_relu(lane_taddr, L.c1, b1, hbuf, row, nullptr, 0);
             tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
@@ -353,6 +374,7 @@ fp_interp_mlp_kernel(const FpArgs a) {
                 tc_fence_before(); group_bar(bar_id);            // every warp has drained D: the next tile's layer 1 may overwrite it
             }
         }
+        if (dbgc) { a.dbg[2] = t_wait_full; a.dbg[3] = t_wait_done; a.dbg[4] = clock64() - t_loop0; a.dbg[5] = nseq; }
     }
     tc_fence_before();
     __syncthreads();
@@ -366,6 +388,12 @@ static void fp_put(__half* base, int R, int r, int k, float v) {
 }  // namespace g4d
 
 using namespace g4d;
+
+static long long* g_fp_dbg = nullptr;
+// Debug aid: device buffer of >= 8 int64 that CTA 0 of the next g4d_fp_interp_mlp launches fills with cycle counters
+// ([0] producer group 0 waiting for a free A buffer, [1] its whole loop, [2] consumer group 0's issuer waiting for a full A
+// buffer, [3] waiting for layer 1's MMAs, [4] its whole loop, [5] tiles of the CTA); NULL switches it off.
+G4D_API void g4d_debug_fp_counters(void* buf) { g_fp_dbg = (long long*)buf; }
 
 G4D_API size_t g4d_fp_param_bytes(const g4d_fp_desc* d) {
     FpLayout L; const char* why = nullptr;
@@ -414,6 +442,7 @@ G4D_API int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int 
     a.ntiles = (int)nt;
     a.dist2 = dist2; a.idx = idx; a.known_pm = (const __half*)known_pm; a.params = (const unsigned char*)params_dev;
     a.out_feat = out_feat; a.out_head = out_head;
+    a.dbg = g_fp_dbg;
     cudaError_t e = cudaFuncSetAttribute(fp_interp_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
     if (e != cudaSuccess) { set_error("fp_interp_mlp: shared memory opt-in (%u B): %s", a.L.total_smem, cudaGetErrorString(e)); return (int)e; }
     cudaFuncSetAttribute(fp_interp_mlp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);

@@ -159,6 +159,9 @@ int g4d_fp_pack_params(const g4d_fp_desc* d, const float* w1, const float* b1, c
 int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int b, int n, int m, const float* dist2, const int* idx,
                       const void* known_pm, float* out_feat, float* out_head, void* stream);
 
+/* debug aid: cycle counters of CTA 0 of the following g4d_fp_interp_mlp launches (buf: >= 8 int64 on the device; NULL = off) */
+void g4d_debug_fp_counters(void* buf);
+
 /* y[b,c,:] = max(y[b,c,:] + bias[c], 0) in place (relu = 0: bias only); channel-major (b,c,n), b*c <= 65535.  One-pass
  * epilogue for the feature-propagation 1x1 convolutions that stay on the library GEMM (pointnet2_modules.py:154). */
 int g4d_bias_relu_inplace(int b, int c, long long n, float* y, const float* bias, int relu, void* stream);
