@@ -17,8 +17,9 @@
 //   consumer groups (2 x 4 warps)  take alternate tiles, each with its own TMEM accumulator (128 columns) and hidden
 //                                  buffer: one lane issues the tcgen05.mma chain (up to four layers), the group's four
 //                                  warps run the epilogues (tcgen05.ld -> bias, ReLU -> fp16 -> shared; layer 2 also
-//                                  writes the FP output, the last layer the logits).  The A buffer is released by the
-//                                  tcgen05.commit of layer 1, so the gather of the following tiles overlaps the chain.
+//                                  writes the FP output, the last layer the logits).  The hidden activations overwrite the
+//                                  tile's A buffer in place; the tcgen05.commit of the last layer returns it to the ring, so
+//                                  with 4 buffers the gather of the next two tiles overlaps the two chains in flight.
 //   Only the FP output (channel-major fp32, returned by the encoder as l_features[0]) and the logits (point-major)
 //   are written to HBM.  (The first version ran gather and layers back to back in one 256-thread CTA with block-wide
 //   barriers: 31 % of its warp samples waited on the gather, 31 % at barriers -- profiles/r01_ncu_summary.md.)
@@ -59,17 +60,23 @@ static bool fp_layout(const g4d_fp_desc* d, FpLayout* L, const char** why) {
     int hmax = L->c1;                                      // widest hidden activation (K of layers 2..4)
     if (L->c2 > hmax) hmax = L->c2;
     if (L->h1 > hmax) hmax = L->h1;
-    L->a_bytes = (uint32_t)FP_TILE * L->c_in * 2;
-    L->h_bytes = (uint32_t)FP_TILE * hmax * 2;
-    L->off_h = (o + 127) / 128 * 128;
-    L->off_meta = L->off_h + FP_CG * L->h_bytes;           // per producer group, double-buffered: 3 point ids + 3 weights per row
-    L->off_bar = L->off_meta + FP_PG * 2 * FP_TILE * 6 * 4;
+    // One ring of buffers serves as layer-1 operand (filled by the producers) AND, in place, as the hidden-activation buffer
+    // of the consumer group that took it: it goes back to the producers when the tile's last MMA has read it.
+    const int kmax = L->c_in > hmax ? L->c_in : hmax;
+    L->a_bytes = (uint32_t)FP_TILE * kmax * 2;
+    L->h_bytes = 0;
+    L->off_h = 0;
+    L->off_meta = (o + 127) / 128 * 128;                   // per producer group, double-buffered: 3 point ids + 3 weights per row
+    L->off_bar = L->off_meta + FP_PG * 3 * FP_TILE * 6 * 4;  // + one raw staging area (cp.async prefetch of dist2 / idx) per group
     L->off_a = (L->off_bar + 8 * (3 + 2 * FP_MAX_A + FP_CG) + 127) / 128 * 128;
-    const uint32_t budget = 227u * 1024u;
-    if (L->off_a + 2 * L->a_bytes > budget) { *why = "fp: shared memory footprint exceeds 227 KB"; return false; }
-    uint32_t na = (budget - L->off_a) / L->a_bytes;
+    // keep ~24 KB of the SM's shared memory free: Nsight Compute cannot replay a kernel that takes all 227 KB (the first
+    // version of this layout did, and every capture of it hung), and the L1 that is left serves the gather
+    const uint32_t budget = 203u * 1024u;
+    if (L->off_a + (FP_CG + 1) * L->a_bytes > 227u * 1024u) { *why = "fp: shared memory footprint exceeds 227 KB"; return false; }
+    uint32_t na = budget > L->off_a ? (budget - L->off_a) / L->a_bytes : 0;
+    if (na < (uint32_t)FP_CG + 1) na = FP_CG + 1;          // each consumer group holds one buffer: at least one more to fill
     L->na = na > (uint32_t)FP_MAX_A ? (uint32_t)FP_MAX_A : na;
-    if (const char* e = getenv("G4D_FP_NA")) { const int v = atoi(e); if (v >= 2 && (uint32_t)v <= L->na) L->na = (uint32_t)v; }   // tuning knob
+    if (const char* e = getenv("G4D_FP_NA")) { const int v = atoi(e); if (v >= FP_CG + 1 && (uint32_t)v <= L->na) L->na = (uint32_t)v; }   // tuning knob
     L->total_smem = L->off_a + L->na * L->a_bytes;
     uint32_t p2 = 32;
     while (p2 < (uint32_t)hmax || p2 < (uint32_t)L->h2p) p2 <<= 1;
@@ -104,28 +111,36 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
     for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
-// TMEM row -> +bias, ReLU, fp16 -> hidden buffer (canonical layout), optionally also fp32 channel-major to global
+// TMEM row -> +bias, ReLU, fp16 -> hidden buffer (canonical layout), optionally also fp32 channel-major to global.
+// NB x 16 columns per step: all tcgen05.ld of a step are in flight before the single wait (the load -> wait -> use chain is
+// the consumer's critical path; every access also queues behind the producers' gather in the LSU data pipe).
+template <int NB>
+__device__ __forceinline__ void fp_epilogue_step(uint32_t taddr, const float* bias, unsigned char* hbuf, int row, int c0,
+                                                 float* gout, size_t gstride) {
+    float v[16 * NB], bv[16 * NB];
+#pragma unroll
+    for (int i = 0; i < 4 * NB; ++i)                            // broadcast LDS.128: 4 per 16 columns instead of 16 LDS.32
+        *reinterpret_cast<float4*>(bv + 4 * i) = *reinterpret_cast<const float4*>(bias + c0 + 4 * i);
+    if (NB == 2) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16 * NB; ++i) v[i] = fmaxf(v[i] + bv[i], 0.f);
+    if (gout) {
+#pragma unroll
+        for (int i = 0; i < 16 * NB; ++i) gout[(size_t)(c0 + i) * gstride] = v[i];     // lanes = consecutive points: coalesced
+    }
+    uint4* dst = reinterpret_cast<uint4*>(hbuf);
+#pragma unroll
+    for (int q = 0; q < 2 * NB; ++q)
+        dst[(size_t)(c0 / 8 + q) * FP_TILE + row] = make_uint4(pack_f16x2(v[8 * q], v[8 * q + 1]), pack_f16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                                 pack_f16x2(v[8 * q + 4], v[8 * q + 5]), pack_f16x2(v[8 * q + 6], v[8 * q + 7]));
+}
+
 __device__ __forceinline__ void fp_epilogue_relu(uint32_t lane_taddr, int ncols, const float* bias, unsigned char* hbuf, int row,
                                                  float* gout /* channel 0 of this row's point, or null */, size_t gstride) {
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
-        float v[16], bv[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)                             // 4 broadcast LDS.128 instead of 16 LDS.32: the LSU data pipe is the scarce unit here
-            *reinterpret_cast<float4*>(bv + 4 * i) = *reinterpret_cast<const float4*>(bias + c0 + 4 * i);
-        tmem_ld16(lane_taddr + c0, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bv[i], 0.f);
-        if (gout) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) gout[(size_t)(c0 + i) * gstride] = v[i];     // lanes = consecutive points: coalesced
-        }
-        uint32_t h[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
-        uint4* dst = reinterpret_cast<uint4*>(hbuf);
-        dst[(size_t)(c0 / 8) * FP_TILE + row] = make_uint4(h[0], h[1], h[2], h[3]);
-        dst[(size_t)(c0 / 8 + 1) * FP_TILE + row] = make_uint4(h[4], h[5], h[6], h[7]);
-    }
+    int c0 = 0;
+#pragma unroll 1
+    for (; c0 + 32 <= ncols; c0 += 32) fp_epilogue_step<2>(lane_taddr, bias, hbuf, row, c0, gout, gstride);
+    if (c0 < ncols) fp_epilogue_step<1>(lane_taddr, bias, hbuf, row, c0, gout, gstride);
 }
 
 // D[128 x N] (+)= A[128 x K] . W[N x K]^T, one tcgen05.mma per 16-wide K step (issued by ONE thread; descriptors advance
@@ -193,52 +208,60 @@ fp_interp_mlp_kernel(const FpArgs a) {
         const int prow = pw * 32 + lane;                         // the row whose meta data this thread prepares
         const int rl = lane & 7, cl = lane >> 3;
         const int nchunk = L.c_in >> 3;
-        uint32_t* meta = reinterpret_cast<uint32_t*>(smem + L.off_meta) + pg * 2 * (FP_TILE * 6);
-        // meta loads of the first tile of this group
-        float d0 = 0.f, d1 = 0.f, d2v = 0.f;
-        int j0 = 0, j1 = 0, j2 = 0;
+        uint32_t* meta = reinterpret_cast<uint32_t*>(smem + L.off_meta) + pg * 3 * (FP_TILE * 6);
+        // Raw dist2 / idx of the row this thread prepares are prefetched one tile ahead with cp.async into the thread's own
+        // six staging words (no registers held across the gather -- they spilled, and the spill store waited for the load).
+        float* raw = reinterpret_cast<float*>(meta + 2 * (FP_TILE * 6)) + prow * 6;
+        const uint32_t s_raw = smem_u32(raw);
         long long Rn = ((long long)blockIdx.x + (long long)pg * gridDim.x) * FP_TILE + prow;
         if (pg < nseq && Rn < a.total_rows) {
             const float* dp = a.dist2 + (size_t)Rn * 3; const int* ip = a.idx + (size_t)Rn * 3;
-            d0 = __ldg(dp); d1 = __ldg(dp + 1); d2v = __ldg(dp + 2); j0 = __ldg(ip); j1 = __ldg(ip + 1); j2 = __ldg(ip + 2);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_raw + 4 * k), "l"(dp + k) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_raw + 12 + 4 * k), "l"(ip + k) : "memory");
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
         int buf = 0;
-        const bool dbgp = a.dbg && blockIdx.x == 0 && pg == 0 && pw == 0 && lane == 0;
-        long long t_wait_empty = 0, t_loop0 = dbgp ? clock64() : 0;
         for (int i = pg; i < nseq; i += FP_PG, buf ^= 1) {
             const long long R = Rn;
             const bool live = R < a.total_rows;
             // ---- interpolation weights of row `prow`, exactly the reference's torch arithmetic (pointnet2_modules.py:141-143)
             uint32_t* rowpt = meta + buf * (FP_TILE * 6);
             float* roww = reinterpret_cast<float*>(rowpt + FP_TILE * 3);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");          // this thread's own staging words have landed
             {
                 uint32_t p0 = 0xFFFFFFFFu, p1 = 0xFFFFFFFFu, p2 = 0xFFFFFFFFu;
                 float w0 = 0.f, w1 = 0.f, w2 = 0.f;
                 if (live) {
-                    const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d0), 1e-8f));
-                    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d1), 1e-8f));
-                    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d2v), 1e-8f));
+                    const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(raw[0]), 1e-8f));
+                    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(raw[1]), 1e-8f));
+                    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(raw[2]), 1e-8f));
                     const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
                     w0 = __fdiv_rn(r0, norm); w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm);
                     const uint32_t base = (uint32_t)((unsigned long long)R / (unsigned)a.n) * (uint32_t)a.m;
-                    p0 = base + (uint32_t)j0; p1 = base + (uint32_t)j1; p2 = base + (uint32_t)j2;
+                    p0 = base + __float_as_uint(raw[3]); p1 = base + __float_as_uint(raw[4]); p2 = base + __float_as_uint(raw[5]);
                 }
                 rowpt[prow] = p0; rowpt[FP_TILE + prow] = p1; rowpt[2 * FP_TILE + prow] = p2;
                 roww[prow] = w0; roww[FP_TILE + prow] = w1; roww[2 * FP_TILE + prow] = w2;
             }
             group_bar(1 + FP_CG + pg);          // meta[buf] complete (it is rewritten two tiles later, after the next barrier)
-            // ---- prefetch the meta loads of this group's next tile: their latency hides behind the gather
+            // ---- prefetch the raw meta data of this group's next tile: the latency hides behind the gather
             Rn = R + (long long)FP_PG * gridDim.x * FP_TILE;
             if (i + FP_PG < nseq && Rn < a.total_rows) {
                 const float* dp = a.dist2 + (size_t)Rn * 3; const int* ip = a.idx + (size_t)Rn * 3;
-                d0 = __ldg(dp); d1 = __ldg(dp + 1); d2v = __ldg(dp + 2); j0 = __ldg(ip); j1 = __ldg(ip + 1); j2 = __ldg(ip + 2);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_raw + 4 * k), "l"(dp + k) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_raw + 12 + 4 * k), "l"(ip + k) : "memory");
+                }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
             // ---- A buffer of this tile
             const int ab = i % NA;
             const uint32_t use = (uint32_t)(i / NA);
-            const long long tw0 = dbgp ? clock64() : 0;
-            mbar_wait(bar_empty + 8 * ab, (use & 1) ^ 1);       // freed by the commit of layer 1 of tile i - NA (first lap passes)
-            if (dbgp) t_wait_empty += clock64() - tw0;
+            mbar_wait(bar_empty + 8 * ab, (use & 1) ^ 1);       // freed by the commit of the last layer of tile i - NA (first lap passes)
             uint4* dst = reinterpret_cast<uint4*>(smem + L.off_a + (size_t)ab * L.a_bytes);
             // ---- gather + interpolate: warp pw owns rows 32pw..32pw+31 in two rounds of 16 rows = 2 groups of 8 rows.
             //      Lane (rl, cl) loads 32 bytes (two 8-channel chunks) per tap with ONE 256-bit load, so that a warp-wide load
@@ -302,7 +325,6 @@ fp_interp_mlp_kernel(const FpArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * ab);
         }
-        if (dbgp) { a.dbg[0] = t_wait_empty; a.dbg[1] = clock64() - t_loop0; }
     } else {
         // =========================== CONSUMERS ==================================================================
         const int cg = warp >> 2;                                // consumer group; its warps own TMEM lane quadrants warp & 3
@@ -310,8 +332,6 @@ fp_interp_mlp_kernel(const FpArgs a) {
         const bool issuer = (warp & 3) == 0 && lane == 0;
         const uint32_t tacc = tmem + (uint32_t)cg * L.tcols;     // this group's accumulator columns
         const uint32_t lane_taddr = tacc + ((uint32_t)((warp & 3) * 32) << 16);
-        unsigned char* hbuf = smem + L.off_h + (size_t)cg * L.h_bytes;
-        const uint32_t s_h = smem_u32(hbuf);
         const uint32_t s_w1 = smem_u32(smem + L.off_w1), s_w2 = smem_u32(smem + L.off_w2), s_w3 = smem_u32(smem + L.off_w3),
                        s_w4 = smem_u32(smem + L.off_w4);
         const uint32_t my_done = bar_done + 8 * cg;
@@ -327,13 +347,14 @@ fp_interp_mlp_kernel(const FpArgs a) {
             const int pt = live ? (int)(R - (long long)cloud * a.n) : 0;
             const int ab = i % NA;
             const uint32_t use = (uint32_t)(i / NA);
-            // ---- layer 1: A buffer -> D ; its commit releases the A buffer to the producers
+            unsigned char* hbuf = smem + L.off_a + (size_t)ab * L.a_bytes;     // layer-1 operand, then (in place) the hidden activations
+            const uint32_t s_h = smem_u32(hbuf);
+            // ---- layer 1: A buffer -> D
             if (issuer) {
                 const long long tw0 = dbgc ? clock64() : 0;
                 mbar_wait_spin(bar_full + 8 * ab, use & 1);
                 if (dbgc) t_wait_full += clock64() - tw0;
-                fp_issue_layer(tacc, smem_u32(smem + L.off_a + (size_t)ab * L.a_bytes), s_w1, L.c_in, L.c1);
-                umma_commit(bar_empty + 8 * ab);
+                fp_issue_layer(tacc, s_h, s_w1, L.c_in, L.c1);
                 umma_commit(my_done);
             }
             __syncwarp();
@@ -344,7 +365,11 @@ fp_interp_mlp_kernel(const FpArgs a) {
             fp_epilogue_relu(lane_taddr, L.c1, b1, hbuf, row, nullptr, 0);
             tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
             // ---- layer 2 (FP output)
-            if (issuer) { fp_issue_layer(tacc, s_h, s_w2, L.c1, L.c2); umma_commit(my_done); }
+            if (issuer) {
+                fp_issue_layer(tacc, s_h, s_w2, L.c1, L.c2);
+                if (!L.h1) umma_commit(bar_empty + 8 * ab);      // last reader of the buffer: back to the producers when it retires
+                umma_commit(my_done);
+            }
             __syncwarp();
             mbar_wait(my_done, phase); phase ^= 1;
             tc_fence_after();
@@ -359,7 +384,11 @@ fp_interp_mlp_kernel(const FpArgs a) {
                 fp_epilogue_relu(lane_taddr, L.h1, b3, hbuf, row, nullptr, 0);
                 tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
                 // ---- head layer 2: logits, no activation
-                if (issuer) { fp_issue_layer(tacc, s_h, s_w4, L.h1, L.h2p); umma_commit(my_done); }
+                if (issuer) {
+                    fp_issue_layer(tacc, s_h, s_w4, L.h1, L.h2p);
+                    umma_commit(bar_empty + 8 * ab);             // last reader of the buffer: back to the producers when it retires
+                    umma_commit(my_done);
+                }
                 __syncwarp();
                 mbar_wait(my_done, phase); phase ^= 1;
                 tc_fence_after();
@@ -391,8 +420,8 @@ using namespace g4d;
 
 static long long* g_fp_dbg = nullptr;
 // Debug aid: device buffer of >= 8 int64 that CTA 0 of the next g4d_fp_interp_mlp launches fills with cycle counters
-// ([0] producer group 0 waiting for a free A buffer, [1] its whole loop, [2] consumer group 0's issuer waiting for a full A
-// buffer, [3] waiting for layer 1's MMAs, [4] its whole loop, [5] tiles of the CTA); NULL switches it off.
+// ([2] consumer group 0's issuer waiting for a full A buffer -- i.e. for the producers --, [3] waiting for layer 1's MMAs,
+// [4] its whole loop, [5] tiles of the CTA; the producers carry no counters: they have no registers to spare); NULL = off.
 G4D_API void g4d_debug_fp_counters(void* buf) { g_fp_dbg = (long long*)buf; }
 
 G4D_API size_t g4d_fp_param_bytes(const g4d_fp_desc* d) {

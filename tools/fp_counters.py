@@ -31,6 +31,5 @@ with torch.no_grad():
     L.g4d_debug_fp_counters(None)
 c = buf.cpu().tolist()
 print(f"NA={os.environ.get('G4D_FP_NA', 'default')}: three_nn + fp_interp_mlp {s.elapsed_time(e):.3f} ms; tiles of CTA 0: {c[5]}")
-print(f"  producer group 0: loop {c[1]} cycles, waiting for a free A buffer {c[0]} ({100.0 * c[0] / max(c[1], 1):.1f} %)")
 print(f"  consumer group 0: loop {c[4]} cycles, issuer waiting for a full A buffer {c[2]} ({100.0 * c[2] / max(c[4], 1):.1f} %), "
       f"waiting for layer-1 MMAs {c[3]} ({100.0 * c[3] / max(c[4], 1):.1f} %)")
