@@ -289,15 +289,6 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 // = the whole 128 x k0 tile outstanding, which is what hides the L2/HBM latency of the gather); then the slices are
                 // handed to the MMA warp in order as their groups complete.
                 const char* srcrow = reinterpret_cast<const char*>(a.feat_pm + (size_t)pt * a.c_in);
-                // Coalesced form of the copies of a pure feature slice: lane l copies chunk (l >> 4) of rows (l & 15) and 16 + (l & 15)
-                // of its warp, i.e. 32 contiguous bytes = ONE sector per row and instruction.  (One thread per row and 16 bytes per
-                // copy touches every 32-byte sector twice, and the L1TEX data pipe spends one wavefront per sector touched.)
-                const int lrow = lane & 15, lch = lane >> 4;
-                const unsigned pt_lo = __shfl_sync(0xFFFFFFFFu, pt, lrow), pt_hi = __shfl_sync(0xFFFFFFFFu, pt, 16 + lrow);
-                const int live_lo = __shfl_sync(0xFFFFFFFFu, (int)live, lrow), live_hi = __shfl_sync(0xFFFFFFFFu, (int)live, 16 + lrow);
-                const char* src_lo = reinterpret_cast<const char*>(a.feat_pm + (size_t)pt_lo * a.c_in) + lch * 16;
-                const char* src_hi = reinterpret_cast<const char*>(a.feat_pm + (size_t)pt_hi * a.c_in) + lch * 16;
-                const uint32_t dco = (uint32_t)lch * (TILE_M * 16) + (uint32_t)((r & ~31) + lrow) * 16;   // + slot base (+ 256 for the upper rows)
                 // (waves of at most min(S, RING) slices: a wave must fit the ring, or waiting for its own slots would deadlock)
                 const int wave = S < RING ? S : RING;
                 uint32_t slot = it % RING, ph = (it / RING) & 1;               // one division per tile; then walked
@@ -310,11 +301,6 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                     mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);           // slot free (first lap passes at once)
                     const uint32_t sdst = s_ring + slot * SLICE_BYTES + (uint32_t)r * 16;
                     uint4* gdst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
-                    if (2 * sl + 1 < nchunk_feat) {
-                        const uint32_t d = s_ring + slot * SLICE_BYTES + dco;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src_lo + (size_t)sl * 32), "r"(live_lo ? 16 : 0) : "memory");
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + 256), "l"(src_hi + (size_t)sl * 32), "r"(live_hi ? 16 : 0) : "memory");
-                    } else
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int c = 2 * sl + h;                               // 16-byte chunk index along K
