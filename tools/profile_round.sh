@@ -22,6 +22,11 @@ if [ "${SKIP_NCU:-0}" != 1 ]; then
   timeout -k 10 420 ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled \
       -k regex:'g4d::(?!fp_interp_mlp)' -f -o $OUT/${TAG}_full python tools/ncu_once.py c3 > $OUT/${TAG}_full_run.log 2>&1
   echo "ncu full exit $?"
+  # gpurun brings back at most 64 MiB: keep the CSV pages and per-kernel hot spots of the big report, not the report itself
+  ncu -i $OUT/${TAG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_full_raw.csv 2>/dev/null
+  ncu -i $OUT/${TAG}_full.ncu-rep --page source --csv > $OUT/${TAG}_full_source.csv 2>/dev/null
+  python tools/ncu_hotspots.py $OUT/${TAG}_full_source.csv 25 > $OUT/${TAG}_full_hotspots.txt 2>&1
+  rm -f $OUT/${TAG}_full.ncu-rep $OUT/${TAG}_full_source.csv
   # ... then fp_interp_mlp on its own (a capture of its first warp-specialised version never returned)
   timeout -k 10 ${FP_NCU_TIMEOUT:-120} ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled \
       -k regex:'g4d::fp_interp_mlp' -f -o $OUT/${TAG}_full_fp python tools/ncu_once.py c3 > $OUT/${TAG}_full_fp_run.log 2>&1
