@@ -218,6 +218,48 @@ fp_interp_concat_kernel(int c2, int c1, int m, int n, const float* __restrict__ 
     }
 }
 
+// Same result as fp_interp_concat_kernel<__half> when the known features are given fp16 POINT-major (b, m, c2) -- the copy every
+// fused level already emits for the next gather: the three taps are three contiguous rows, read 8 channels per 16-byte load
+// (the channel-major form gathers 3 scattered words per channel and was instruction-bound: 64 % SM busy at 18 % of DRAM).
+__global__ void __launch_bounds__(256)
+fp_interp_concat_pm_kernel(int c2, int c1, int m, int n, const float* __restrict__ dist2, const int* __restrict__ idx,
+                           const __half* __restrict__ known_pm, const float* __restrict__ skip, __half* __restrict__ out,
+                           long long out_cs, long long out_bs) {
+    const size_t bi = blockIdx.z;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= n) return;
+    __half* o = out + bi * out_bs + pt;
+    const int nch8 = c2 >> 3;
+    if ((int)blockIdx.y < nch8) {
+        const int* id = idx + (bi * n + pt) * 3;
+        const float* d2 = dist2 + (bi * n + pt) * 3;
+        const int i0 = __ldg(id), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+        const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2)), 1e-8f));
+        const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 1)), 1e-8f));
+        const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d2 + 2)), 1e-8f));
+        const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+        const uint4* q0 = reinterpret_cast<const uint4*>(known_pm + (bi * m + i0) * (size_t)c2);
+        const uint4* q1 = reinterpret_cast<const uint4*>(known_pm + (bi * m + i1) * (size_t)c2);
+        const uint4* q2 = reinterpret_cast<const uint4*>(known_pm + (bi * m + i2) * (size_t)c2);
+#pragma unroll 2
+        for (int ch8 = blockIdx.y; ch8 < nch8; ch8 += gridDim.y) {
+            const uint4 a = __ldg(q0 + ch8), b = __ldg(q1 + ch8), c = __ldg(q2 + ch8);
+            const __half2* ha = reinterpret_cast<const __half2*>(&a);
+            const __half2* hb = reinterpret_cast<const __half2*>(&b);
+            const __half2* hc = reinterpret_cast<const __half2*>(&c);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f0 = __half22float2(ha[e]), f1 = __half22float2(hb[e]), f2 = __half22float2(hc[e]);
+                store_out(o + (size_t)(ch8 * 8 + 2 * e) * out_cs, __fmaf_rn(w2, f2.x, __fmaf_rn(w0, f0.x, __fmul_rn(w1, f1.x))));
+                store_out(o + (size_t)(ch8 * 8 + 2 * e + 1) * out_cs, __fmaf_rn(w2, f2.y, __fmaf_rn(w0, f0.y, __fmul_rn(w1, f1.y))));
+            }
+        }
+    }
+    for (int ci = blockIdx.y; ci < c1; ci += gridDim.y)
+        store_out(o + (size_t)(c2 + ci) * out_cs, __ldg(skip + (bi * c1 + ci) * (size_t)n + pt));
+}
+
 // y (c, len) fp16: y[ch, :] = act(y[ch, :] + bias[ch]) in place, 8 halves per thread (len % 8 == 0)
 __global__ void __launch_bounds__(256)
 bias_relu_h_kernel(long long len8, int relu, uint4* __restrict__ y, const float* __restrict__ bias) {
@@ -329,6 +371,18 @@ G4D_API int g4d_fp_interp_concat_cbn_h(int b, int c2, int c1, int m, int n, cons
     fp_interp_concat_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(c2, c1, m, n, dist2, idx, known_feats, skip, (__half*)out_h,
                                                                             (long long)b * n, (long long)n);
     return finish_launch("g4d fp_interp_concat_cbn_h");
+}
+
+G4D_API int g4d_fp_interp_concat_pm_cbn_h(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const void* known_pm_h,
+                                          const float* skip, void* out_h, void* stream) {
+    const int rc = fp_interp_concat_check(b, c2, c1, m, n, dist2, idx, (const float*)known_pm_h, skip, out_h);
+    if (rc) return rc < 0 ? 0 : rc;
+    if (c2 % 8 || ((uintptr_t)known_pm_h & 15)) return bad_arg("fp_interp_concat_pm: c2 must be a multiple of 8 and known_pm 16-byte aligned");
+    const int work = (c2 / 8 > c1 ? c2 / 8 : c1);
+    dim3 grid((n + 255) / 256, work < 4 ? (work < 1 ? 1 : work) : 4, b);
+    fp_interp_concat_pm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c2, c1, m, n, dist2, idx, (const __half*)known_pm_h, skip, (__half*)out_h,
+                                                                     (long long)b * n, (long long)n);
+    return finish_launch("g4d fp_interp_concat_pm_cbn_h");
 }
 
 G4D_API int g4d_bias_relu_h(int c, long long len, void* y_h, const float* bias, int relu, void* stream) {

@@ -46,6 +46,7 @@ class Pointnet2MSGSEG(nn.Module):
         self.FP_modules.append(PointnetFPModule(mlp=[256 + c1, 256, 128], bn=bn))
         self.FP_modules.append(PointnetFPModule(mlp=[c3 + c2, 512, 256], bn=bn))
         self.FP_modules[1].emit_point_major = True     # its output feeds the fused finest-level kernel (fp16 point-major gather)
+        self.FP_modules[2].emit_point_major = True     # ... and this one feeds FP_modules[1]'s interpolation the same way
         self.FC_layer = nn.Sequential(pt_utils.Conv1d(64, 32, bn=True), nn.Dropout(),
                                       pt_utils.Conv1d(32, class_num, activation=None))           # pointnet2encoder.py:98-101
 

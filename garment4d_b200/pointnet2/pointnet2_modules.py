@@ -230,8 +230,14 @@ class PointnetFPModule(nn.Module):
                 # as the TF32 convolutions torch runs by default), bias+ReLU passes are ours, the last layer's GEMM returns
                 # fp32 and its epilogue writes the reference layout (B, C, n) (+ the fp16 point-major copy for the next level).
                 x = torch.empty(c2 + c1, B * n, dtype=torch.float16, device=dev)
-                rc = L.g4d_fp_interp_concat_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(known_feats), _lib.ptr(skip),
-                                                  _lib.ptr(x), _lib.stream_ptr())
+                kpm = getattr(known_feats, "_g4d_pm", None)      # fp16 point-major copy emitted by the producing level
+                if (kpm is not None and c2 % 8 == 0 and kpm.dtype == torch.float16 and tuple(kpm.shape) == (B, m, c2)
+                        and kpm.is_contiguous()):
+                    rc = L.g4d_fp_interp_concat_pm_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kpm), _lib.ptr(skip),
+                                                         _lib.ptr(x), _lib.stream_ptr())
+                else:
+                    rc = L.g4d_fp_interp_concat_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(known_feats), _lib.ptr(skip),
+                                                      _lib.ptr(x), _lib.stream_ptr())
                 _lib.check(rc, "g4d_fp_interp_concat_cbn_h")
                 layers = folded["half"]
                 for li, (w16, b) in enumerate(layers):

@@ -177,6 +177,10 @@ int g4d_fp_interp_concat(int b, int c2, int c1, int m, int n, const float* dist2
  * (Cout x Cin) . (Cin x b*n) GEMM for the module's 1x1 convolutions (pointnet2_modules.py:153-154). */
 int g4d_fp_interp_concat_cbn_h(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const float* known_feats,
                                const float* skip, void* out_h, void* stream);
+/* g4d_fp_interp_concat_cbn_h with the known features given fp16 point-major, known_pm_h (b, m, c2), c2 % 8 == 0 (the copy
+ * the fused levels emit for the next gather): three contiguous rows per point instead of 3 scattered words per channel. */
+int g4d_fp_interp_concat_pm_cbn_h(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const void* known_pm_h,
+                                  const float* skip, void* out_h, void* stream);
 /* y (c, len) fp16, in place: y[ch,:] = max(y[ch,:] + bias[ch], 0) (relu = 0: bias only); len % 8 == 0 */
 int g4d_bias_relu_h(int c, long long len, void* y_h, const float* bias, int relu, void* stream);
 /* epilogue of the last layer of that route: yin (c, b, n) pre-activations (fp32, or fp16 when in_half) ->

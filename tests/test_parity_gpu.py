@@ -311,6 +311,16 @@ def test_fp_batched_gemm_route_entry_points(cuda):
     _lib.check(L.g4d_fp_interp_concat_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kf), _lib.ptr(skip), _lib.ptr(xh),
                                             _lib.stream_ptr()), "g4d_fp_interp_concat_cbn_h")
     assert torch.equal(xh.view(c2 + c1, B, n), ref.permute(1, 0, 2).to(torch.float16))
+    # point-major fp16 source: identical to the channel-major kernel run on the fp16-rounded features
+    kpm = kf.transpose(1, 2).to(torch.float16).contiguous()
+    kf_r = kpm.float().transpose(1, 2).contiguous()
+    x_cm = torch.zeros(c2 + c1, B * n, dtype=torch.float16, device=cuda)
+    _lib.check(L.g4d_fp_interp_concat_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kf_r), _lib.ptr(skip), _lib.ptr(x_cm),
+                                            _lib.stream_ptr()), "g4d_fp_interp_concat_cbn_h")
+    x_pm = torch.zeros_like(x_cm)
+    _lib.check(L.g4d_fp_interp_concat_pm_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kpm), _lib.ptr(skip), _lib.ptr(x_pm),
+                                               _lib.stream_ptr()), "g4d_fp_interp_concat_pm_cbn_h")
+    assert torch.equal(x_pm, x_cm)
     # bias + ReLU on (c, len) fp16
     C, ln = 37, 8 * 123
     y0 = _t((rs.randn(C, ln) * 3).astype(np.float16), cuda)

@@ -150,10 +150,13 @@ def test_fp_module_eval_routes_vs_operator_sequence(cuda, spec):
     finally:
         torch.backends.cudnn.allow_tf32 = old
     with torch.no_grad():
-        for route in ("half", "conv"):
-            prev, pm._FP_GEMM = pm._FP_GEMM, route
+        for route in ("half", "half+pm", "conv"):
+            prev, pm._FP_GEMM = pm._FP_GEMM, route.split("+")[0]
+            kin = kf.clone()
+            if route == "half+pm" and c2 % 8 == 0:      # known features with the fp16 point-major copy the fused levels attach
+                kin._g4d_pm = kin.transpose(1, 2).to(torch.float16).contiguous()
             try:
-                out = mod(unknown, known, skip, kf)
+                out = mod(unknown, known, skip, kin)
             finally:
                 pm._FP_GEMM = prev
             assert out.shape == ref.shape and out.dtype == torch.float32
