@@ -61,6 +61,9 @@ _SIGNATURES = {
     "g4d_fp_interp_concat": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_fp_interp_concat_cbn_h": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_fp_interp_concat_pm_cbn_h": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_fp_interp_concat_rows_h": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_bias_relu_rows_h": (_i, [ctypes.c_longlong, _i, _vp, _vp, _i, _vp]),
+    "g4d_bias_relu_rows_unpack": (_i, [_i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "g4d_bias_relu_h": (_i, [_i, ctypes.c_longlong, _vp, _vp, _i, _vp]),
     "g4d_bias_relu_unpack": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "g4d_bias_relu_pm": (_i, [_i, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -260,6 +260,105 @@ fp_interp_concat_pm_kernel(int c2, int c1, int m, int n, const float* __restrict
         store_out(o + (size_t)(c2 + ci) * out_cs, __ldg(skip + (bi * c1 + ci) * (size_t)n + pt));
 }
 
+// Point-major form of the FP-module front half: known_pm (b, m, c2) and skip_pm (b, n, c1) fp16 point-major (the copies the
+// fused levels emit) -> out (b*n, c2 + c1) fp16 row-major, the activation operand of `x @ W^T`.  A warp handles 4 points x 8
+// lanes; lane j of a point moves the 16-byte chunks j, j+8, ... of its row, so every load and store instruction of the warp
+// covers full 128-byte segments, and a block writes one contiguous 32 x (c2+c1) x 2 byte region (the (C, b*n) layout wrote
+// 64-byte pieces 480 KB apart: 0.9 TB/s).  Weights: lanes 0..2 of a point each take one tap (one sqrt, two divides, the same
+// correctly rounded operations in the same order as everywhere else), results shared by shuffles.
+__global__ void __launch_bounds__(256)
+fp_interp_concat_rows_kernel(int c2, int c1, int m, int n, const float* __restrict__ dist2, const int* __restrict__ idx,
+                             const __half* __restrict__ known_pm, const __half* __restrict__ skip_pm, __half* __restrict__ out) {
+    const size_t bi = blockIdx.y;
+    const int lane = threadIdx.x & 31, j = lane & 7, gbase = lane & ~7;
+    const int pt = blockIdx.x * 32 + (threadIdx.x >> 3);
+    const bool live = pt < n;
+    float r = 0.f;
+    int it = 0;
+    if (live && j < 3) {
+        r = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + (bi * n + pt) * 3 + j)), 1e-8f));
+        it = __ldg(idx + (bi * n + pt) * 3 + j);
+    }
+    const float r0 = __shfl_sync(0xFFFFFFFFu, r, gbase), r1 = __shfl_sync(0xFFFFFFFFu, r, gbase + 1), r2 = __shfl_sync(0xFFFFFFFFu, r, gbase + 2);
+    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+    const int i0 = __shfl_sync(0xFFFFFFFFu, it, gbase), i1 = __shfl_sync(0xFFFFFFFFu, it, gbase + 1), i2 = __shfl_sync(0xFFFFFFFFu, it, gbase + 2);
+    if (!live) return;
+    const int ctot = c2 + c1;
+    uint4* orow = reinterpret_cast<uint4*>(out + (bi * n + pt) * (size_t)ctot);
+    const uint4* q0 = reinterpret_cast<const uint4*>(known_pm + (bi * m + i0) * (size_t)c2);
+    const uint4* q1 = reinterpret_cast<const uint4*>(known_pm + (bi * m + i1) * (size_t)c2);
+    const uint4* q2 = reinterpret_cast<const uint4*>(known_pm + (bi * m + i2) * (size_t)c2);
+    const int nch2 = c2 >> 3, nch1 = c1 >> 3;
+#pragma unroll 2
+    for (int ch = j; ch < nch2; ch += 8) {
+        const uint4 a = __ldg(q0 + ch), b = __ldg(q1 + ch), c = __ldg(q2 + ch);
+        const __half2* ha = reinterpret_cast<const __half2*>(&a);
+        const __half2* hb = reinterpret_cast<const __half2*>(&b);
+        const __half2* hc = reinterpret_cast<const __half2*>(&c);
+        uint4 o;
+        __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f0 = __half22float2(ha[e]), f1 = __half22float2(hb[e]), f2 = __half22float2(hc[e]);
+            const float vx = __fmaf_rn(w2, f2.x, __fmaf_rn(w0, f0.x, __fmul_rn(w1, f1.x)));
+            const float vy = __fmaf_rn(w2, f2.y, __fmaf_rn(w0, f0.y, __fmul_rn(w1, f1.y)));
+            ho[e] = __floats2half2_rn(fminf(fmaxf(vx, -65504.f), 65504.f), fminf(fmaxf(vy, -65504.f), 65504.f));
+        }
+        orow[ch] = o;
+    }
+    if (nch1) {
+        const uint4* srow = reinterpret_cast<const uint4*>(skip_pm + (bi * n + pt) * (size_t)c1);
+        for (int ch = j; ch < nch1; ch += 8) orow[nch2 + ch] = __ldg(srow + ch);
+    }
+}
+
+// y (rows, c) fp16 row-major, in place: y[r, ch] = act(y[r, ch] + bias[ch]); c % 8 == 0
+__global__ void __launch_bounds__(256)
+bias_relu_rows_h_kernel(long long total8, int c8, int relu, uint4* __restrict__ y, const float* __restrict__ bias) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c8) * 8;
+        uint4 v = y[i];
+        __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 f = __half22float2(h[k]);
+            f.x += __ldg(bias + ch + 2 * k); f.y += __ldg(bias + ch + 2 * k + 1);
+            if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+            h[k] = __floats2half2_rn(fminf(f.x, 65504.f), fminf(f.y, 65504.f));
+        }
+        y[i] = v;
+    }
+}
+
+// Last layer of the point-major route: yin (b, n, c) fp32 pre-activations -> out_cm (b, c, n) fp32 = act(yin + bias) (the
+// reference layout) and, optionally, the same values fp16 point-major out_pm (b, n, c).  32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256)
+bias_relu_rows_unpack_kernel(int c, int n, int relu, const float* __restrict__ yin, const float* __restrict__ bias,
+                             float* __restrict__ out_cm, __half* __restrict__ out_pm) {
+    __shared__ float tile[32][33];
+    const size_t bi = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int pt = p0 + ty + 8 * r, ch = c0 + tx;
+        float v = 0.f;
+        if (ch < c && pt < n) {
+            v = __ldg(yin + (bi * n + pt) * (size_t)c + ch) + __ldg(bias + ch);
+            if (relu) v = fmaxf(v, 0.f);
+            if (out_pm) out_pm[(bi * n + pt) * (size_t)c + ch] = __float2half_rn(fminf(v, 65504.f));
+        }
+        tile[ty + 8 * r][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ch = c0 + ty + 8 * r, pt = p0 + tx;
+        if (ch < c && pt < n) out_cm[(bi * c + ch) * (size_t)n + pt] = tile[tx][ty + 8 * r];
+    }
+}
+
 // y (c, len) fp16: y[ch, :] = act(y[ch, :] + bias[ch]) in place, 8 halves per thread (len % 8 == 0)
 __global__ void __launch_bounds__(256)
 bias_relu_h_kernel(long long len8, int relu, uint4* __restrict__ y, const float* __restrict__ bias) {
@@ -383,6 +482,43 @@ G4D_API int g4d_fp_interp_concat_pm_cbn_h(int b, int c2, int c1, int m, int n, c
     fp_interp_concat_pm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c2, c1, m, n, dist2, idx, (const __half*)known_pm_h, skip, (__half*)out_h,
                                                                      (long long)b * n, (long long)n);
     return finish_launch("g4d fp_interp_concat_pm_cbn_h");
+}
+
+G4D_API int g4d_fp_interp_concat_rows_h(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const void* known_pm_h,
+                                        const void* skip_pm_h, void* out_rows_h, void* stream) {
+    if (b < 0 || c2 < 0 || c1 < 0 || n < 0 || m < 0) return bad_arg("fp_interp_concat_rows: negative size");
+    if (b == 0 || n == 0 || c2 + c1 == 0) return 0;
+    if (!out_rows_h || (c2 > 0 && (!dist2 || !idx || !known_pm_h || m == 0)) || (c1 > 0 && !skip_pm_h)) return bad_arg("fp_interp_concat_rows: null pointer");
+    if (c2 % 8 || c1 % 8) return bad_arg("fp_interp_concat_rows: c2 and c1 must be multiples of 8");
+    if (((uintptr_t)known_pm_h | (uintptr_t)skip_pm_h | (uintptr_t)out_rows_h) & 15) return bad_arg("fp_interp_concat_rows: pointers must be 16-byte aligned");
+    if (b > 65535) return bad_arg("fp_interp_concat_rows: b > 65535");
+    dim3 grid((n + 31) / 32, b);
+    fp_interp_concat_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c2, c1, m, n, dist2, idx, (const __half*)known_pm_h,
+                                                                       (const __half*)skip_pm_h, (__half*)out_rows_h);
+    return finish_launch("g4d fp_interp_concat_rows_h");
+}
+
+G4D_API int g4d_bias_relu_rows_h(long long rows, int c, void* y_h, const float* bias, int relu, void* stream) {
+    if (rows < 0 || c < 0) return bad_arg("bias_relu_rows_h: negative size");
+    if (rows == 0 || c == 0) return 0;
+    if (!y_h || !bias) return bad_arg("bias_relu_rows_h: null pointer");
+    if (c % 8 || ((uintptr_t)y_h & 15)) return bad_arg("bias_relu_rows_h: c must be a multiple of 8 and y 16-byte aligned");
+    const long long total8 = rows * (c / 8);
+    long long blocks = (total8 + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    bias_relu_rows_h_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total8, c / 8, relu, (uint4*)y_h, bias);
+    return finish_launch("g4d bias_relu_rows_h");
+}
+
+G4D_API int g4d_bias_relu_rows_unpack(int b, int c, int n, const float* yin_rows, const float* bias, int relu, float* out_cm, void* out_pm,
+                                      void* stream) {
+    if (b < 0 || c < 0 || n < 0) return bad_arg("bias_relu_rows_unpack: negative size");
+    if (b == 0 || c == 0 || n == 0) return 0;
+    if (!yin_rows || !bias || !out_cm) return bad_arg("bias_relu_rows_unpack: null pointer");
+    if (b > 65535 || (c + 31) / 32 > 65535) return bad_arg("bias_relu_rows_unpack: b or c/32 > 65535");
+    dim3 grid((n + 31) / 32, (c + 31) / 32, b);
+    bias_relu_rows_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, relu, yin_rows, bias, out_cm, (__half*)out_pm);
+    return finish_launch("g4d bias_relu_rows_unpack");
 }
 
 G4D_API int g4d_bias_relu_h(int c, long long len, void* y_h, const float* bias, int relu, void* stream) {

@@ -229,8 +229,33 @@ class PointnetFPModule(nn.Module):
                 # written fp16 in (C, B*n) layout, hidden layers stay fp16 (fp32 accumulation; same 11-bit operand precision
                 # as the TF32 convolutions torch runs by default), bias+ReLU passes are ours, the last layer's GEMM returns
                 # fp32 and its epilogue writes the reference layout (B, C, n) (+ the fp16 point-major copy for the next level).
-                x = torch.empty(c2 + c1, B * n, dtype=torch.float16, device=dev)
                 kpm = getattr(known_feats, "_g4d_pm", None)      # fp16 point-major copy emitted by the producing level
+                spm = None if unknow_feats is None else getattr(unknow_feats, "_g4d_pm", None)
+                pm_ok = lambda t, shape: (t is not None and t.dtype == torch.float16 and tuple(t.shape) == shape and t.is_contiguous())
+                layers = folded["half"]
+                if (pm_ok(kpm, (B, m, c2)) and (c1 == 0 or pm_ok(spm, (B, n, c1))) and c2 % 8 == 0 and c1 % 8 == 0
+                        and all(w.shape[0] % 8 == 0 for w, _ in layers[:-1])):
+                    # point-major all the way: x (B*n, C) rows -> x @ W^T per layer (the library's linear-layer form)
+                    x = torch.empty(B * n, c2 + c1, dtype=torch.float16, device=dev)
+                    rc = L.g4d_fp_interp_concat_rows_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kpm), _lib.ptr(spm),
+                                                       _lib.ptr(x), _lib.stream_ptr())
+                    _lib.check(rc, "g4d_fp_interp_concat_rows_h")
+                    for li, (w16, b) in enumerate(layers):
+                        if li < len(layers) - 1:
+                            x = F.linear(x, w16)
+                            rc = L.g4d_bias_relu_rows_h(B * n, w16.shape[0], _lib.ptr(x), _lib.ptr(b), 1, _lib.stream_ptr())
+                            _lib.check(rc, "g4d_bias_relu_rows_h")
+                        else:
+                            y = torch.mm(x, w16.t(), out_dtype=torch.float32)
+                            out = torch.empty(B, w16.shape[0], n, dtype=torch.float32, device=dev)
+                            pm = torch.empty(B, n, w16.shape[0], dtype=torch.float16, device=dev) if self.emit_point_major else None
+                            rc = L.g4d_bias_relu_rows_unpack(B, w16.shape[0], n, _lib.ptr(y), _lib.ptr(b), 1, _lib.ptr(out), _lib.ptr(pm),
+                                                             _lib.stream_ptr())
+                            _lib.check(rc, "g4d_bias_relu_rows_unpack")
+                            if pm is not None:
+                                out._g4d_pm = pm
+                    return out
+                x = torch.empty(c2 + c1, B * n, dtype=torch.float16, device=dev)
                 if (kpm is not None and c2 % 8 == 0 and kpm.dtype == torch.float16 and tuple(kpm.shape) == (B, m, c2)
                         and kpm.is_contiguous()):
                     rc = L.g4d_fp_interp_concat_pm_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kpm), _lib.ptr(skip),
@@ -239,7 +264,6 @@ class PointnetFPModule(nn.Module):
                     rc = L.g4d_fp_interp_concat_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(known_feats), _lib.ptr(skip),
                                                       _lib.ptr(x), _lib.stream_ptr())
                 _lib.check(rc, "g4d_fp_interp_concat_cbn_h")
-                layers = folded["half"]
                 for li, (w16, b) in enumerate(layers):
                     if li < len(layers) - 1:
                         x = torch.mm(w16, x)

@@ -181,6 +181,16 @@ int g4d_fp_interp_concat_cbn_h(int b, int c2, int c1, int m, int n, const float*
  * the fused levels emit for the next gather): three contiguous rows per point instead of 3 scattered words per channel. */
 int g4d_fp_interp_concat_pm_cbn_h(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const void* known_pm_h,
                                   const float* skip, void* out_h, void* stream);
+/* Point-major form of the same front half: known_pm_h (b, m, c2) and skip_pm_h (b, n, c1) fp16 point-major (NULL with c1 = 0),
+ * c2 % 8 == c1 % 8 == 0 -> out_rows_h (b*n, c2+c1) fp16 row-major = the activation operand of x @ W^T. */
+int g4d_fp_interp_concat_rows_h(int b, int c2, int c1, int m, int n, const float* dist2, const int* idx, const void* known_pm_h,
+                                const void* skip_pm_h, void* out_rows_h, void* stream);
+/* y (rows, c) fp16 row-major, in place: y[r,ch] = max(y[r,ch] + bias[ch], 0) (relu = 0: bias only); c % 8 == 0 */
+int g4d_bias_relu_rows_h(long long rows, int c, void* y_h, const float* bias, int relu, void* stream);
+/* last layer of that route: yin_rows (b, n, c) fp32 pre-activations -> out_cm (b, c, n) fp32 = act(yin + bias) and, when
+ * out_pm != NULL, the same values fp16 point-major (b, n, c) */
+int g4d_bias_relu_rows_unpack(int b, int c, int n, const float* yin_rows, const float* bias, int relu, float* out_cm, void* out_pm,
+                              void* stream);
 /* y (c, len) fp16, in place: y[ch,:] = max(y[ch,:] + bias[ch], 0) (relu = 0: bias only); len % 8 == 0 */
 int g4d_bias_relu_h(int c, long long len, void* y_h, const float* bias, int relu, void* stream);
 /* epilogue of the last layer of that route: yin (c, b, n) pre-activations (fp32, or fp16 when in_half) ->

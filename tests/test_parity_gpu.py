@@ -321,6 +321,27 @@ def test_fp_batched_gemm_route_entry_points(cuda):
     _lib.check(L.g4d_fp_interp_concat_pm_cbn_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kpm), _lib.ptr(skip), _lib.ptr(x_pm),
                                                _lib.stream_ptr()), "g4d_fp_interp_concat_pm_cbn_h")
     assert torch.equal(x_pm, x_cm)
+    # point-major rows route: same values as the (C, B*n) operand, transposed; then its two epilogues
+    spm = skip.transpose(1, 2).to(torch.float16).contiguous()
+    x_rows = torch.zeros(B * n, c2 + c1, dtype=torch.float16, device=cuda)
+    _lib.check(L.g4d_fp_interp_concat_rows_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kpm), _lib.ptr(spm), _lib.ptr(x_rows),
+                                             _lib.stream_ptr()), "g4d_fp_interp_concat_rows_h")
+    assert torch.equal(x_rows.t().contiguous(), x_cm)
+    yr0 = _t((rs.randn(B * n, 24) * 3).astype(np.float16), cuda)
+    b24 = _t(rs.randn(24).astype(np.float32), cuda)
+    yr = yr0.clone()
+    _lib.check(L.g4d_bias_relu_rows_h(B * n, 24, _lib.ptr(yr), _lib.ptr(b24), 1, _lib.stream_ptr()), "g4d_bias_relu_rows_h")
+    assert torch.equal(yr, torch.relu(yr0.float() + b24[None, :]).to(torch.float16))
+    for (Bq, Cq, nq) in [(2, 128, 1024), (3, 50, 77)]:
+        yin = _t((rs.randn(Bq, nq, Cq) * 3).astype(np.float32), cuda)
+        bq = _t(rs.randn(Cq).astype(np.float32), cuda)
+        out = torch.zeros(Bq, Cq, nq, dtype=torch.float32, device=cuda)
+        pmq = torch.zeros(Bq, nq, Cq, dtype=torch.float16, device=cuda)
+        _lib.check(L.g4d_bias_relu_rows_unpack(Bq, Cq, nq, _lib.ptr(yin), _lib.ptr(bq), 1, _lib.ptr(out), _lib.ptr(pmq), _lib.stream_ptr()),
+                   "g4d_bias_relu_rows_unpack")
+        want = torch.relu(yin + bq[None, None, :])
+        assert torch.equal(out, want.transpose(1, 2).contiguous())
+        assert torch.equal(pmq, want.to(torch.float16))
     # bias + ReLU on (c, len) fp16
     C, ln = 37, 8 * 123
     y0 = _t((rs.randn(C, ln) * 3).astype(np.float16), cuda)

@@ -153,10 +153,13 @@ def test_fp_module_eval_routes_vs_operator_sequence(cuda, spec):
         for route in ("half", "half+pm", "conv"):
             prev, pm._FP_GEMM = pm._FP_GEMM, route.split("+")[0]
             kin = kf.clone()
-            if route == "half+pm" and c2 % 8 == 0:      # known features with the fp16 point-major copy the fused levels attach
+            sin = None if skip is None else skip.clone()
+            if route == "half+pm" and c2 % 8 == 0:      # features with the fp16 point-major copies the fused levels attach
                 kin._g4d_pm = kin.transpose(1, 2).to(torch.float16).contiguous()
+                if sin is not None:
+                    sin._g4d_pm = sin.transpose(1, 2).to(torch.float16).contiguous()       # -> the point-major rows route
             try:
-                out = mod(unknown, known, skip, kin)
+                out = mod(unknown, known, sin, kin)
             finally:
                 pm._FP_GEMM = prev
             assert out.shape == ref.shape and out.dtype == torch.float32
