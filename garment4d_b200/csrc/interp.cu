@@ -313,17 +313,31 @@ fp_interp_concat_rows_kernel(int c2, int c1, int m, int n, const float* __restri
     }
 }
 
-// y (rows, c) fp16 row-major, in place: y[r, ch] = act(y[r, ch] + bias[ch]); c % 8 == 0
+// y (rows, c) fp16 row-major, in place: y[r, ch] = act(y[r, ch] + bias[ch]); c % 8 == 0.  FIXED_CH: the grid stride is a
+// multiple of c/8 (always the case when 256 % (c/8) == 0), so a thread sees the same 8 channels in every iteration and keeps
+// their biases in registers (no modulo, no bias loads in the loop).
+template <bool FIXED_CH>
 __global__ void __launch_bounds__(256)
 bias_relu_rows_h_kernel(long long total8, int c8, int relu, uint4* __restrict__ y, const float* __restrict__ bias) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % c8) * 8;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float bv[8];
+    if (FIXED_CH) {
+        const int ch = (int)(i0 % c8) * 8;
+        *reinterpret_cast<float4*>(bv) = __ldg(reinterpret_cast<const float4*>(bias + ch));
+        *reinterpret_cast<float4*>(bv + 4) = __ldg(reinterpret_cast<const float4*>(bias + ch + 4));
+    }
+    for (long long i = i0; i < total8; i += (long long)gridDim.x * blockDim.x) {
+        if (!FIXED_CH) {
+            const int ch = (int)(i % c8) * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bv[k] = __ldg(bias + ch + k);
+        }
         uint4 v = y[i];
         __half2* h = reinterpret_cast<__half2*>(&v);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float2 f = __half22float2(h[k]);
-            f.x += __ldg(bias + ch + 2 * k); f.y += __ldg(bias + ch + 2 * k + 1);
+            f.x += bv[2 * k]; f.y += bv[2 * k + 1];
             if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
             h[k] = __floats2half2_rn(fminf(f.x, 65504.f), fminf(f.y, 65504.f));
         }
@@ -506,7 +520,10 @@ G4D_API int g4d_bias_relu_rows_h(long long rows, int c, void* y_h, const float* 
     const long long total8 = rows * (c / 8);
     long long blocks = (total8 + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    bias_relu_rows_h_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total8, c / 8, relu, (uint4*)y_h, bias);
+    if (256 % (c / 8) == 0 && ((uintptr_t)bias & 15) == 0)
+        bias_relu_rows_h_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total8, c / 8, relu, (uint4*)y_h, bias);
+    else
+        bias_relu_rows_h_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total8, c / 8, relu, (uint4*)y_h, bias);
     return finish_launch("g4d bias_relu_rows_h");
 }
 

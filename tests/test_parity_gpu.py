@@ -327,11 +327,12 @@ def test_fp_batched_gemm_route_entry_points(cuda):
     _lib.check(L.g4d_fp_interp_concat_rows_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kpm), _lib.ptr(spm), _lib.ptr(x_rows),
                                              _lib.stream_ptr()), "g4d_fp_interp_concat_rows_h")
     assert torch.equal(x_rows.t().contiguous(), x_cm)
-    yr0 = _t((rs.randn(B * n, 24) * 3).astype(np.float16), cuda)
-    b24 = _t(rs.randn(24).astype(np.float32), cuda)
-    yr = yr0.clone()
-    _lib.check(L.g4d_bias_relu_rows_h(B * n, 24, _lib.ptr(yr), _lib.ptr(b24), 1, _lib.stream_ptr()), "g4d_bias_relu_rows_h")
-    assert torch.equal(yr, torch.relu(yr0.float() + b24[None, :]).to(torch.float16))
+    for cw in (24, 64, 256):          # 24: generic path (modulo per element); 64, 256: biases held in registers
+        yr0 = _t((rs.randn(B * n, cw) * 3).astype(np.float16), cuda)
+        bw = _t(rs.randn(cw).astype(np.float32), cuda)
+        yr = yr0.clone()
+        _lib.check(L.g4d_bias_relu_rows_h(B * n, cw, _lib.ptr(yr), _lib.ptr(bw), 1, _lib.stream_ptr()), "g4d_bias_relu_rows_h")
+        assert torch.equal(yr, torch.relu(yr0.float() + bw[None, :]).to(torch.float16))
     for (Bq, Cq, nq) in [(2, 128, 1024), (3, 50, 77)]:
         yin = _t((rs.randn(Bq, nq, Cq) * 3).astype(np.float32), cuda)
         bq = _t(rs.randn(Cq).astype(np.float32), cuda)
