@@ -59,23 +59,28 @@ class EncoderLBSRunner:
 
     @torch.no_grad()
     def forward_host(self, pc_pin, betas_pin, pose_pin, labels_pin, verts_pin, joints_pin):
-        """End to end with pinned HOST buffers: per chunk H2D -> encoder + lbs -> argmax labels (uint8) -> D2H into the
-        given pinned outputs.  Asynchronous: synchronise the current stream (or the device) before reading the outputs."""
+        """End to end with pinned HOST buffers: per chunk H2D of the clouds -> encoder -> argmax labels (uint8) -> D2H; the SMPL
+        parameters go up, lbs() runs for all frames and the posed vertices / joints (90 % of the result bytes) come back on the
+        lbs stream, overlapped with the encoder.  Asynchronous: synchronise the current stream (or the device) before reading
+        the outputs."""
         C = pc_pin.shape[0]
         cur = torch.cuda.current_stream(self.device)
+        self.lbs_stream.wait_stream(cur)
+        with torch.cuda.stream(self.lbs_stream):
+            bt = betas_pin.to(self.device, non_blocking=True)
+            ps = pose_pin.to(self.device, non_blocking=True)
+            v, j = glbs.lbs(bt, ps, *self.smpl)
+            verts_pin.copy_(v, non_blocking=True)
+            joints_pin.copy_(j, non_blocking=True)
         for (lo, hi), st in zip(self._bounds(C), self.streams):
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 pc = pc_pin[lo:hi].to(self.device, non_blocking=True)
-                bt = betas_pin[lo:hi].to(self.device, non_blocking=True)
-                ps = pose_pin[lo:hi].to(self.device, non_blocking=True)
                 _, sem, _, _ = self.model(pc)
-                v, j = glbs.lbs(bt, ps, *self.smpl)
                 labels_pin[lo:hi].copy_(sem.argmax(dim=2).to(torch.uint8), non_blocking=True)   # the segmentation the model consumes (mesh_encoder.py:113)
-                verts_pin[lo:hi].copy_(v, non_blocking=True)
-                joints_pin[lo:hi].copy_(j, non_blocking=True)
         for st in self.streams:
             cur.wait_stream(st)
+        cur.wait_stream(self.lbs_stream)
 
 
 class GraphedEncoderLBSRunner(EncoderLBSRunner):
