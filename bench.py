@@ -304,6 +304,21 @@ def main():
         dist.destroy_process_group()
 
 
+def ncu_traffic(ncu_rows, key):
+    """DRAM bytes of one launch from the rows of profiles/*_ncu_summary.json.  key = (kernel-name substring, occurrence) or a
+    list of such pairs whose launches together make up the operator (summed); None / not captured -> None."""
+    if key is None or not ncu_rows:
+        return None
+    keys = key if isinstance(key, list) else [key]
+    total = 0.0
+    for sub, occ in keys:
+        hits = [r for r in ncu_rows if sub in r["kernel"]]
+        if occ >= len(hits) or hits[occ].get("traffic_bytes") is None:
+            return None
+        total += hits[occ]["traffic_bytes"]
+    return total
+
+
 def kernel_breakdown(torch, L, model, pc, betas, pose, smpl, flush, peaks, C, N, reps=5):
     """Per-kernel device time (CUDA events on the launching stream, L2 flushed before each launch) and the
     algorithmic-work roofline of each (bytes / flops per cloud from SURVEY.md section 8(d))."""
@@ -335,11 +350,7 @@ def kernel_breakdown(torch, L, model, pc, betas, pose, smpl, flush, peaks, C, N,
             ncu_rows = json.load(open(cands[-1]))
 
     def traffic(key):
-        if key is None:
-            return None
-        sub, occ = key
-        hits = [r for r in ncu_rows if sub in r["kernel"]]
-        return hits[occ]["traffic_bytes"] if occ < len(hits) else None
+        return ncu_traffic(ncu_rows, key)
 
     def hbm(name, ms, bytes_per_cloud, note="", ncu=None):
         ach = bytes_per_cloud * C / (ms * 1e-3) / 1e9
@@ -368,10 +379,13 @@ def kernel_breakdown(torch, L, model, pc, betas, pose, smpl, flush, peaks, C, N,
             idxs = pu.ball_query_pair(g0.radius, g0.nsample, g1.radius, g1.nsample, xyz, new_xyz)
             c_in = 0 if feats is None else feats.shape[1]
             # the north star's fused ball-query+group operator (materialises the grouped tensor; not on the fused route)
-            for g in (g0, g1):
+            for gi, g in enumerate((g0, g1)):
                 ms = t(lambda: pu.QueryAndGroup(g.radius, g.nsample)(xyz, new_xyz, feats))
+                # the operator = one ball query (grid kernel at level 0, brute force below) + the fused grouping pass
+                bq = ("ball_query_grid_kernel<1>", gi) if lvl == 0 else ("ball_query_kernel<1>", 2 * (lvl - 1) + gi)
                 hbm(f"query_and_group L{lvl} K={g.nsample}", ms,
-                    12 * n_in + 12 * P + 4 * c_in * n_in + 4 * P * g.nsample + 4 * (c_in + 3) * P * g.nsample)
+                    12 * n_in + 12 * P + 4 * c_in * n_in + 4 * P * g.nsample + 4 * (c_in + 3) * P * g.nsample,
+                    ncu=[bq, ("group_fused_kernel", 2 * lvl + gi)])
             new_xyz2, new_feats = sa(xyz, feats)
             feat_pm = None if feats is None else getattr(feats, "_g4d_pm")
             ctot = new_feats.shape[1]

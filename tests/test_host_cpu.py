@@ -194,3 +194,20 @@ def test_sharding_world2_gloo(tmp_path):
     assert res["cover"] == [1] * 7            # every sequence owned by exactly one rank
     assert res["tmax"] == 11.0                # max over ranks, as bench.py reports
     assert res["lo_hi"] == [0, 4]
+
+
+def test_bench_reads_ncu_traffic_from_committed_profiles():
+    """bench.py's roofline.traffic comes from profiles/*_ncu_summary.json: the lookups it makes must resolve."""
+    import glob
+    import json
+    import bench
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_summary.json")))
+    assert cands, "no committed ncu summary"
+    rows = json.load(open(cands[-1]))
+    for key in [("fps_pruned_kernel<512", 0), ("ball_query_grid_kernel<2>", 0), ("sa_mlp_max_kernel<32, 1, ", 1), ("fp_interp_mlp_kernel", 0),
+                ("three_nn_grid_kernel", 0), [("ball_query_grid_kernel<1>", 1), ("group_fused_kernel", 1)],
+                [("ball_query_kernel<1>", 3), ("group_fused_kernel", 5)]]:
+        v = bench.ncu_traffic(rows, key)
+        assert v is not None and v > 0, key
+    assert bench.ncu_traffic(rows, ("no_such_kernel", 0)) is None
+    assert bench.ncu_traffic(rows, None) is None and bench.ncu_traffic([], ("fps", 0)) is None

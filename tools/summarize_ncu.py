@@ -4,7 +4,7 @@ file under profiles/: per launch duration, DRAM bytes (read + write = `roofline.
 utilisation, occupancy, registers, shared memory and the top warp-stall reasons.
 
     ncu -i gpurun_out/r01a_full.ncu-rep --page raw --csv > /tmp/raw.csv
-    python tools/summarize_ncu.py /tmp/raw.csv profiles/r01_ncu_summary
+    python tools/summarize_ncu.py /tmp/raw.csv [/tmp/newer_raw.csv ...] profiles/r01_ncu_summary [--drop REGEX]
 """
 import csv
 import json
@@ -20,7 +20,7 @@ def short(name):
     return (m.group(1) + (m.group(2) or "")) if m else re.sub(r"\(.*", "", name)[:80]
 
 
-def main(raw_csv, out_prefix):
+def load(raw_csv):
     rows = list(csv.reader(open(raw_csv)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
@@ -56,6 +56,19 @@ def main(raw_csv, out_prefix):
             "smem_dyn": val(r, "launch__shared_mem_per_block_dynamic"), "smem_static": val(r, "launch__shared_mem_per_block_static"),
             "top_stalls": [f"{n} {v:.2f}" for v, n in stalls[:3]],
         })
+    return out
+
+
+def main(raw_csvs, out_prefix, drop=None):
+    """raw_csvs: one or more raw pages; kernels of a later file replace the same-named kernels of the earlier ones (a newer
+    capture of a kernel that changed since); `drop`: regex of kernel names to leave out (no longer launched on the default path)."""
+    out = []
+    for path in raw_csvs:
+        new = load(path)
+        names = {k["kernel"] for k in new}
+        out = [k for k in out if k["kernel"] not in names] + new
+    if drop:
+        out = [k for k in out if not re.search(drop, k["kernel"])]
     json.dump(out, open(out_prefix + ".json", "w"), indent=1)
     f = lambda v, fmt="%.1f": "-" if v is None else fmt % v
     with open(out_prefix + ".md", "w") as md:
@@ -72,4 +85,10 @@ def main(raw_csv, out_prefix):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    args = sys.argv[1:]
+    drop = None
+    if "--drop" in args:
+        i = args.index("--drop")
+        drop = args[i + 1]
+        del args[i:i + 2]
+    main(args[:-1], args[-1], drop)
