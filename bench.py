@@ -270,7 +270,7 @@ def main():
         kernels = kernel_breakdown(torch, L, model, pc_dev, betas_dev, pose_dev, smpl, flush, peaks, C, N)
         if rank == 0 and kernels:
             top = max((k for k in kernels if k.get("roofline")), key=lambda k: k["ms"])
-            roof = dict(top["roofline"], kernel=top["name"], ms_per_launch=top["ms"], peak_source=peaks["source"])
+            roof = dict(top["roofline"], kernel=top["name"], ms_per_launch=top["ms"], peak_source=peaks["source"], note=top.get("note", ""))
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
