@@ -211,3 +211,42 @@ def test_bench_reads_ncu_traffic_from_committed_profiles():
         assert v is not None and v > 0, key
     assert bench.ncu_traffic(rows, ("no_such_kernel", 0)) is None
     assert bench.ncu_traffic(rows, None) is None and bench.ncu_traffic([], ("fps", 0)) is None
+
+
+def test_fp_param_packing_layout():
+    """g4d_fp_pack_params (host function, no GPU): the four weight matrices as UMMA canonical K-major images, fp32 biases behind
+    them, class rows padded to 16; and the descriptor checks."""
+    from garment4d_b200 import _lib
+    L = _lib.lib()
+    c_in, c1, c2, h1, h2 = 128, 128, 64, 32, 7
+    d = _lib.FpDesc(c_in, c1, c2, h1, h2)
+    nbytes = L.g4d_fp_param_bytes(ctypes.byref(d))
+    h2p = 16
+    assert nbytes == 2 * (c_in * c1 + c1 * c2 + c2 * h1 + h1 * h2p) + 4 * (c1 + c2 + h1 + h2p)
+    rs = np.random.RandomState(1)
+    w1, w2, w3, w4 = (rs.randn(c1, c_in).astype(np.float32), rs.randn(c2, c1).astype(np.float32), rs.randn(h1, c2).astype(np.float32),
+                      rs.randn(h2, h1).astype(np.float32))
+    b1, b2, b3, b4 = (rs.randn(c).astype(np.float32) for c in (c1, c2, h1, h2))
+    blob = np.zeros(nbytes, np.uint8)
+    rc = L.g4d_fp_pack_params(ctypes.byref(d), *(a.ctypes.data for a in (w1, b1, w2, b2, w3, b3, w4, b4)), blob.ctypes.data)
+    assert rc == 0
+
+    def canon(off, rows, k):                                     # [k/8][row][k%8] fp16 -> (row, k) fp32
+        img = blob[off:off + 2 * rows * k].view(np.float16).reshape(k // 8, rows, 8)
+        return img.transpose(1, 0, 2).reshape(rows, k).astype(np.float32), off + 2 * rows * k
+
+    h = lambda a: a.astype(np.float16).astype(np.float32)
+    W1, o = canon(0, c1, c_in)
+    W2, o = canon(o, c2, c1)
+    W3, o = canon(o, h1, c2)
+    W4, o = canon(o, h2p, h1)
+    assert np.array_equal(W1, h(w1)) and np.array_equal(W2, h(w2)) and np.array_equal(W3, h(w3))
+    assert np.array_equal(W4[:h2], h(w4)) and not W4[h2:].any()              # padded class rows are zero
+    for b, n in ((b1, c1), (b2, c2), (b3, h1)):
+        assert np.array_equal(blob[o:o + 4 * n].view(np.float32), b)
+        o += 4 * n
+    assert np.array_equal(blob[o:o + 4 * h2].view(np.float32), b4) and not blob[o + 4 * h2:o + 4 * h2p].any()
+    # no head: h1 = 0 drops the head matrices; bad widths are refused with a message
+    assert L.g4d_fp_param_bytes(ctypes.byref(_lib.FpDesc(c_in, c1, c2, 0, 0))) == 2 * (c_in * c1 + c1 * c2) + 4 * (c1 + c2)
+    assert L.g4d_fp_param_bytes(ctypes.byref(_lib.FpDesc(c_in, 100, c2, h1, h2))) == 0 and b"multiples of 16" in L.g4d_last_error()
+    assert L.g4d_fp_param_bytes(ctypes.byref(_lib.FpDesc(c_in, c1, c2, h1, 17))) == 0
