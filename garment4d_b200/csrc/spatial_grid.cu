@@ -15,6 +15,7 @@
 //
 // Work drops from N*P (8192*1024 per cloud at SA1) distance tests to ~a few hundred per query.
 #include <float.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "grid.cuh"
 
@@ -331,6 +332,101 @@ three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const 
     oi[0] = (int)(unsigned)k1; oi[1] = (int)(unsigned)k2; oi[2] = (int)(unsigned)k3;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-cooperative form of the same search (EXPERIMENTAL: selected with G4D_NN_COOP=1, not yet validated on the GPU).
+// three_nn_grid_kernel is instruction-bound: 3840 warp instructions per 32 points with 14 of 32 lanes active, because every
+// lane walks its own shells of cells.  Here a warp takes 32 unknown points that are neighbours in the cell-sorted order of
+// `ugrid`, visits the block of cells of the KNOWN grid that covers all of them plus one ring, and stages each run of
+// candidates once in shared memory; every lane then scans the same list (uniform control flow, broadcast reads) keeping its
+// three smallest (d, k) keys -- the same total order, so the same result whatever the visiting order.  A lane is done when its
+// third-best distance is below its distance to the faces of the visited block (same conservative 0.998 margin as above); if
+// any lane is not, the block grows by one ring and only the NEW cells are scanned (every known point is seen exactly once).
+constexpr int NNC_WARPS = 8;
+
+__global__ void __launch_bounds__(NNC_WARPS * 32)
+three_nn_coop_kernel(int n, int m, const float* __restrict__ unknown_all, const float* __restrict__ kgrid_all,
+                     const float* __restrict__ ugrid_all, float* __restrict__ dist2_all, int* __restrict__ idx_all) {
+    __shared__ float4 stage[NNC_WARPS][32];
+    const size_t cloud = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t0 = (blockIdx.x * NNC_WARPS + warp) * 32;
+    if (t0 >= n) return;                                             // warp-uniform
+    const int t = t0 + lane;
+    const bool live = t < n;
+    const float* g = kgrid_all + cloud * grid_cloud_words(m);
+    const GridHdr H = *grid_hdr(g);
+    const int* cell_start = grid_cell_start(g);
+    const float4* sorted = grid_sorted(g);
+    int pt = 0;
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    int cx = 0, cy = 0, cz = 0;
+    if (live) {
+        pt = __float_as_int(__ldg(&grid_sorted(ugrid_all + cloud * grid_cloud_words(n))[t].w));
+        const float* u = unknown_all + (cloud * n + pt) * 3;
+        ux = __ldg(u); uy = __ldg(u + 1); uz = __ldg(u + 2);
+        cx = cell_coord(ux, H.ox, H.inv_h, H.dx); cy = cell_coord(uy, H.oy, H.inv_h, H.dy); cz = cell_coord(uz, H.oz, H.inv_h, H.dz);
+    }
+    const unsigned FULL = 0xFFFFFFFFu;
+    // block of cells covering the warp's points, plus one ring (lane 0 is always live: t0 < n)
+    int rx0 = max(__reduce_min_sync(FULL, live ? cx : 0x7FFFFFFF) - 1, 0), rx1 = min(__reduce_max_sync(FULL, live ? cx : -1) + 1, H.dx - 1);
+    int ry0 = max(__reduce_min_sync(FULL, live ? cy : 0x7FFFFFFF) - 1, 0), ry1 = min(__reduce_max_sync(FULL, live ? cy : -1) + 1, H.dy - 1);
+    int rz0 = max(__reduce_min_sync(FULL, live ? cz : 0x7FFFFFFF) - 1, 0), rz1 = min(__reduce_max_sync(FULL, live ? cz : -1) + 1, H.dz - 1);
+    int px0 = 0, px1 = -1, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;       // previously visited block: empty
+    const unsigned long long EMPTY = 0x7F80000000000000ull;
+    unsigned long long k1 = EMPTY, k2 = EMPTY, k3 = EMPTY;
+    for (;;) {
+        for (int zz = rz0; zz <= rz1; ++zz)
+            for (int yy = ry0; yy <= ry1; ++yy) {
+                const bool seen_row = zz >= pz0 && zz <= pz1 && yy >= py0 && yy <= py1;      // its cells px0..px1 were visited before
+                const int row = (zz * H.dy + yy) * H.dx;
+                for (int sgm = 0; sgm < (seen_row ? 2 : 1); ++sgm) {
+                    const int xa = !seen_row ? rx0 : (sgm == 0 ? rx0 : px1 + 1);
+                    const int xb = !seen_row ? rx1 : (sgm == 0 ? px0 - 1 : rx1);
+                    if (xa > xb) continue;
+                    const int beg = __ldg(cell_start + row + xa), end = __ldg(cell_start + row + xb + 1);
+                    for (int j0 = beg; j0 < end; j0 += 32) {
+                        const int cnt = min(32, end - j0);
+                        __syncwarp();                                 // the previous batch has been consumed by every lane
+                        if (lane < cnt) stage[warp][lane] = __ldg(sorted + j0 + lane);
+                        __syncwarp();
+                        for (int c = 0; c < cnt; ++c) {
+                            const float4 p = stage[warp][c];          // broadcast read
+                            const unsigned long long key = nn_key(sqdist_ref(ux - p.x, uy - p.y, uz - p.z), __float_as_int(p.w));
+                            if (key < k3) {
+                                k3 = key;
+                                if (k3 < k2) { const unsigned long long tmp = k2; k2 = k3; k3 = tmp; }
+                                if (k2 < k1) { const unsigned long long tmp = k1; k1 = k2; k2 = tmp; }
+                            }
+                        }
+                    }
+                }
+            }
+        const bool whole = rx0 == 0 && ry0 == 0 && rz0 == 0 && rx1 == H.dx - 1 && ry1 == H.dy - 1 && rz1 == H.dz - 1;
+        if (whole) break;
+        // every unvisited known point lies beyond a face of the visited block on a side where the grid continues
+        float bound = INFINITY;
+        if (rx0 > 0) bound = fminf(bound, ux - (H.ox + (float)rx0 * H.h));
+        if (rx1 < H.dx - 1) bound = fminf(bound, (H.ox + (float)(rx1 + 1) * H.h) - ux);
+        if (ry0 > 0) bound = fminf(bound, uy - (H.oy + (float)ry0 * H.h));
+        if (ry1 < H.dy - 1) bound = fminf(bound, (H.oy + (float)(ry1 + 1) * H.h) - uy);
+        if (rz0 > 0) bound = fminf(bound, uz - (H.oz + (float)rz0 * H.h));
+        if (rz1 < H.dz - 1) bound = fminf(bound, (H.oz + (float)(rz1 + 1) * H.h) - uz);
+        bound = fmaxf(bound, 0.f);
+        const bool done = !live || __uint_as_float((unsigned)(k3 >> 32)) < bound * bound * 0.998f;
+        if (__all_sync(FULL, done)) break;
+        px0 = rx0; px1 = rx1; py0 = ry0; py1 = ry1; pz0 = rz0; pz1 = rz1;
+        rx0 = max(rx0 - 1, 0); rx1 = min(rx1 + 1, H.dx - 1);
+        ry0 = max(ry0 - 1, 0); ry1 = min(ry1 + 1, H.dy - 1);
+        rz0 = max(rz0 - 1, 0); rz1 = min(rz1 + 1, H.dz - 1);
+    }
+    if (live) {
+        float* od = dist2_all + (cloud * n + pt) * 3;
+        int* oi = idx_all + (cloud * n + pt) * 3;
+        od[0] = __uint_as_float((unsigned)(k1 >> 32)); od[1] = __uint_as_float((unsigned)(k2 >> 32)); od[2] = __uint_as_float((unsigned)(k3 >> 32));
+        oi[0] = (int)(unsigned)k1; oi[1] = (int)(unsigned)k2; oi[2] = (int)(unsigned)k3;
+    }
+}
+
 }  // namespace g4d
 
 using namespace g4d;
@@ -382,6 +478,10 @@ G4D_API int g4d_three_nn_grid(int b, int n, int m, const float* unknown, const v
     if (b == 0 || n == 0) return 0;
     if (!unknown || !known_grid || !dist2 || !idx) return bad_arg("three_nn_grid: null pointer");
     dim3 gridDim((n + 255) / 256, b);
-    three_nn_grid_kernel<<<gridDim, 256, 0, (cudaStream_t)stream>>>(n, m, unknown, (const float*)known_grid, (const float*)unknown_grid, dist2, idx);
+    static const bool coop = getenv("G4D_NN_COOP") && atoi(getenv("G4D_NN_COOP")) == 1;      // experimental, off by default
+    if (coop && unknown_grid && m > 0)
+        three_nn_coop_kernel<<<gridDim, NNC_WARPS * 32, 0, (cudaStream_t)stream>>>(n, m, unknown, (const float*)known_grid, (const float*)unknown_grid, dist2, idx);
+    else
+        three_nn_grid_kernel<<<gridDim, 256, 0, (cudaStream_t)stream>>>(n, m, unknown, (const float*)known_grid, (const float*)unknown_grid, dist2, idx);
     return finish_launch("g4d three_nn_grid");
 }
