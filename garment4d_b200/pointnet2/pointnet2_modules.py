@@ -28,6 +28,7 @@ from . import pytorch_utils as pt_utils
 # Feature-propagation MLPs in eval mode: "half" = one fp16 library GEMM per layer over the whole batch (default),
 # "conv" = per-cloud fp32/TF32 library convolution.  Both with our prologue / bias+ReLU epilogue kernels.
 _FP_GEMM = os.environ.get("G4D_FP_GEMM", "half")
+_FP_LT_EPILOGUE = os.environ.get("G4D_FP_LT_EPILOGUE", "0") == "1"
 
 
 def _as_point_major_half(features: torch.Tensor) -> torch.Tensor:
@@ -242,6 +243,10 @@ class PointnetFPModule(nn.Module):
                     _lib.check(rc, "g4d_fp_interp_concat_rows_h")
                     for li, (w16, b) in enumerate(layers):
                         if li < len(layers) - 1:
+                            if _FP_LT_EPILOGUE:
+                                # EXPERIMENTAL (G4D_FP_LT_EPILOGUE=1, not yet measured): bias + ReLU in the library GEMM's epilogue
+                                x = torch._addmm_activation(b.to(torch.float16), x, w16.t(), use_gelu=False)
+                                continue
                             x = F.linear(x, w16)
                             rc = L.g4d_bias_relu_rows_h(B * n, w16.shape[0], _lib.ptr(x), _lib.ptr(b), 1, _lib.stream_ptr())
                             _lib.check(rc, "g4d_bias_relu_rows_h")
