@@ -250,3 +250,10 @@ def test_fp_param_packing_layout():
     assert L.g4d_fp_param_bytes(ctypes.byref(_lib.FpDesc(c_in, c1, c2, 0, 0))) == 2 * (c_in * c1 + c1 * c2) + 4 * (c1 + c2)
     assert L.g4d_fp_param_bytes(ctypes.byref(_lib.FpDesc(c_in, 100, c2, h1, h2))) == 0 and b"multiples of 16" in L.g4d_last_error()
     assert L.g4d_fp_param_bytes(ctypes.byref(_lib.FpDesc(c_in, c1, c2, h1, 17))) == 0
+
+
+def test_encoder_marks_the_fp_levels_that_feed_fused_gathers():
+    """The two coarser FP levels emit the fp16 point-major copy their consumer gathers from; the finest one does not."""
+    from garment4d_b200.encoder import Pointnet2MSGSEG
+    m = Pointnet2MSGSEG(input_channels=0, bn=True, global_feat=False)
+    assert [fp.emit_point_major for fp in m.FP_modules] == [False, True, True]
