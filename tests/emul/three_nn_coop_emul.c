@@ -74,10 +74,9 @@ static int imax(int a, int b) { return a > b ? a : b; }
 
 /* one cloud: unknown (n,3), known (m,3); ucell / kcell: the min_cell arguments of the two grids.
  * dist2 (n,3), idx (n,3) out; returns the total number of candidate visits (work measure), passes_out = growth rounds summed */
-long long three_nn_coop_emul(int n, int m, const float* unknown, const float* known, float ucell, float kcell, float* dist2, int* idx,
-                             long long* passes_out) {
-    Grid U, K;
-    grid_build(n, unknown, ucell, &U);
+static long long coop_core(int n, int m, const float* unknown, const float* known, const int* order, float kcell, float* dist2, int* idx,
+                           long long* passes_out) {
+    Grid K;
     grid_build(m, known, kcell, &K);
     const Hdr H = K.H;
     const uint64_t EMPTY = 0x7F80000000000000ull;
@@ -91,7 +90,7 @@ long long three_nn_coop_emul(int n, int m, const float* unknown, const float* kn
             live[l] = t0 + l < n; pt[l] = 0; ux[l] = uy[l] = uz[l] = 0.f; cx[l] = cy[l] = cz[l] = 0;
             k1[l] = k2[l] = k3[l] = EMPTY;
             if (live[l]) {
-                int32_t kk; memcpy(&kk, &U.sorted[4 * (size_t)(t0 + l) + 3], 4); pt[l] = kk;
+                int32_t kk = order[t0 + l]; pt[l] = kk;
                 ux[l] = unknown[3 * kk]; uy[l] = unknown[3 * kk + 1]; uz[l] = unknown[3 * kk + 2];
                 cx[l] = cell_coord(ux[l], H.ox, H.inv_h, H.dx); cy[l] = cell_coord(uy[l], H.oy, H.inv_h, H.dy); cz[l] = cell_coord(uz[l], H.oz, H.inv_h, H.dz);
                 X0 = imin(X0, cx[l]); X1 = imax(X1, cx[l]); Y0 = imin(Y0, cy[l]); Y1 = imax(Y1, cy[l]); Z0 = imin(Z0, cz[l]); Z1 = imax(Z1, cz[l]);
@@ -154,7 +153,24 @@ long long three_nn_coop_emul(int n, int m, const float* unknown, const float* kn
                 oi[0] = (int)(uint32_t)k1[l]; oi[1] = (int)(uint32_t)k2[l]; oi[2] = (int)(uint32_t)k3[l];
             }
     }
-    free(U.sorted); free(K.sorted);
+    free(K.sorted);
     if (passes_out) *passes_out = passes;
     return visits;
+}
+
+long long three_nn_coop_emul(int n, int m, const float* unknown, const float* known, float ucell, float kcell, float* dist2, int* idx,
+                             long long* passes_out) {
+    Grid U;
+    grid_build(n, unknown, ucell, &U);
+    int* order = (int*)malloc(sizeof(int) * (n > 0 ? n : 1));
+    for (int t = 0; t < n; ++t) { int32_t kk; memcpy(&kk, &U.sorted[4 * (size_t)t + 3], 4); order[t] = kk; }
+    const long long v = coop_core(n, m, unknown, known, order, kcell, dist2, idx, passes_out);
+    free(order); free(U.sorted);
+    return v;
+}
+
+/* the same search with an explicit processing order of the unknown points (to study other orders, e.g. Morton) */
+long long three_nn_coop_emul_order(int n, int m, const float* unknown, const float* known, const int* order, float kcell, float* dist2,
+                                   int* idx, long long* passes_out) {
+    return coop_core(n, m, unknown, known, order, kcell, dist2, idx, passes_out);
 }
