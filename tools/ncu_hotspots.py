@@ -12,6 +12,7 @@ def main(path, top=40):
     rows = list(csv.reader(open(path)))
     # several kernels may be concatenated: each starts with a "Kernel Name" row followed by a header row
     i = 0
+    seen = None
     while i < len(rows):
         if rows[i] and rows[i][0] == "Kernel Name":
             name, hdr = rows[i][1], rows[i + 1]
@@ -21,7 +22,9 @@ def main(path, top=40):
                 if len(rows[j]) >= len(hdr) - 2:
                     body.append(rows[j])
                 j += 1
-            report(name, hdr, body, top)
+            if (name, body) != seen:          # the CSV repeats each kernel (one block per source view): report it once
+                report(name, hdr, body, top)
+            seen = (name, body)
             i = j
         else:
             i += 1
