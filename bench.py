@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying the captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
+    ap.add_argument("--seed-rank", type=int, default=None, help="debug: generate the synthetic inputs of this rank (single-GPU repro of a multi-GPU run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -187,7 +188,7 @@ def main():
 
     B, T, N = CONFIGS[args.config]
     C = B * T
-    seed = 1234 + 1000 * int(args.config[1]) + rank
+    seed = 1234 + 1000 * int(args.config[1]) + (rank if args.seed_rank is None else args.seed_rank)
     torch.manual_seed(1234)                     # same weights on every rank
     model = Pointnet2MSGSEG(input_channels=0, bn=True, global_feat=False).to(dev).eval()
     smpl_np = synthetic.synthetic_smpl(seed=1234)

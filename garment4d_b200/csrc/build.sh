@@ -10,7 +10,9 @@ mkdir -p "$HERE/obj"
 pids=()
 for f in "$HERE"/*.cu; do
     o="$HERE/obj/$(basename "${f%.cu}").o"
-    if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/umma.cuh" -nt "$o" ] || [ "${1:-}" = "--force" ]; then
+    stale=0
+    for h in "$HERE"/*.cuh "$HERE"/../../include/*.h "$HERE/build.sh"; do [ "$h" -nt "$o" ] && stale=1; done
+    if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ $stale = 1 ] || [ "${1:-}" = "--force" ]; then
         ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; exit 1; } ) &
         pids+=($!)
     fi

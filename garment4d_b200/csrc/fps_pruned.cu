@@ -182,10 +182,6 @@ template <int T, int PPT>
 static int launch_fps_pruned(int b, int n, int m, int lg, const float* grid, int* idx, float* new_xyz, cudaStream_t s) {
     auto kern = fps_pruned_kernel<T, PPT>;
     size_t smem = (size_t)T * PPT * (3 * sizeof(float) + sizeof(unsigned short));
-    // EXPERIMENTAL scheduling knob (off by default, not yet measured): G4D_FPS_OCC=1 pads the request so that only ONE cloud is
-    // resident per SM (a cloud alone takes 0.93 us per step, two per SM 1.29 us each) and other kernels can share the SM.
-    static const bool one_per_sm = getenv("G4D_FPS_OCC") && atoi(getenv("G4D_FPS_OCC")) == 1;
-    if (one_per_sm && smem < 120 * 1024) smem = 120 * 1024;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("fps_pruned: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);

@@ -12,7 +12,8 @@ struct GridHdr {
     float ox, oy, oz, inv_h;
     int dx, dy, dz, ncells;
     float h;
-    int pad[7];
+    float eps;                               // absolute slack >= any rounding error of a cell-face coordinate or of the binning (8 ulp of max |coord|)
+    int pad[6];
 };
 static_assert(sizeof(GridHdr) == GRID_HDR * 4, "GridHdr layout");
 

@@ -69,15 +69,24 @@ grid_build_kernel(int n, const float* __restrict__ xyz_all, float min_cell, floa
         if (sane) {
             for (int it = 0; it < 200; ++it) {
                 const float fx = floorf(ex / h) + 1.f, fy = floorf(ey / h) + 1.f, fz = floorf(ez / h) + 1.f;
-                if (fx * fy * fz <= (float)GRID_MAX_CELLS) { dx = (int)fx; dy = (int)fy; dz = (int)fz; break; }
+                if (fx * fy * fz <= (float)GRID_MAX_CELLS && fmaxf(fx, fmaxf(fy, fz)) <= 256.f) { dx = (int)fx; dy = (int)fy; dz = (int)fz; break; }
                 h *= 1.25f;
                 if (it == 199) { dx = dy = dz = 1; }
             }
         }
+        // Rounding.  (1) Binning: c = floor((v - o) * inv_h) carries a relative error of ~3 * 2^-24, i.e. up to cells_per_axis *
+        // 1.8e-7 cells; with at most 256 cells per axis (enforced above) that is < 5e-5 cells, inside the 1e-4 * h head-room of the
+        // cell edge over the search radius, so a hit is never more than one cell away.  (2) The cell faces o + c*h used for culling
+        // carry an absolute error of a few ulp of the largest coordinate, and a point may sit up to 5e-5 * h outside the faces of
+        // the cell it was binned to: the searches subtract hdr.eps from every face gap they cull with.
+        float amax = 0.f;
+        for (int a = 0; a < 3; ++a) amax = fmaxf(amax, fmaxf(fabsf(L[a]), fabsf(H[a])));
+        const float eps = sane ? amax * 9.5367431640625e-07f + 1e-4f * h : 0.f;      // 2^-20 * max|coord| (8 ulp) + binning slack
         hdr.ox = sane ? L[0] : 0.f; hdr.oy = sane ? L[1] : 0.f; hdr.oz = sane ? L[2] : 0.f;
         hdr.h = h; hdr.inv_h = (dx * dy * dz > 1) ? 1.0f / h : 0.f;
         hdr.dx = dx; hdr.dy = dy; hdr.dz = dz; hdr.ncells = dx * dy * dz;
-        for (int i = 0; i < 7; ++i) hdr.pad[i] = 0;
+        hdr.eps = eps;
+        for (int i = 0; i < 6; ++i) hdr.pad[i] = 0;
         *reinterpret_cast<GridHdr*>(g) = hdr;
     }
     __syncthreads();
@@ -162,10 +171,10 @@ ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_x
                 const float fy0 = H.oy + (float)cy * H.h, fz0 = H.oz + (float)cz * H.h, fx0 = H.ox + (float)cx * H.h;
                 const float gy = oy < 0 ? qy - fy0 : (oy > 0 ? (fy0 + H.h) - qy : 0.f);
                 const float gz = oz < 0 ? qz - fz0 : (oz > 0 ? (fz0 + H.h) - qz : 0.f);
-                const float gyp = fmaxf(gy, 0.f), gzp = fmaxf(gz, 0.f);
+                const float gyp = fmaxf(gy - H.eps, 0.f), gzp = fmaxf(gz - H.eps, 0.f);
                 const float rem = r2max * 1.001f - gyp * gyp - gzp * gzp;
                 if (rem >= 0.f && H.inv_h > 0.f) {
-                    const float gxl = fmaxf(qx - fx0, 0.f), gxr = fmaxf((fx0 + H.h) - qx, 0.f);
+                    const float gxl = fmaxf(qx - fx0 - H.eps, 0.f), gxr = fmaxf((fx0 + H.h) - qx - H.eps, 0.f);
                     const int xa = (gxl * gxl > rem) ? cx : x0;          // left neighbour cell cannot hold a hit
                     const int xb = (gxr * gxr > rem) ? cx : x1;
                     const int row = (zz * H.dy + yy) * H.dx;
@@ -285,9 +294,9 @@ three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const 
         for (int zz = max(cz - R, 0); zz <= min(cz + R, H.dz - 1); ++zz) {
             const bool zshell = (zz == cz - R) || (zz == cz + R);
             // distance from the query to the slab of cells zz (0 inside the query's own slab; conservative when clamped)
-            const float gz = zz < cz ? fmaxf(uz - (fz0 - (float)(cz - zz - 1) * H.h), 0.f) : (zz > cz ? fmaxf((fz0 + (float)(zz - cz) * H.h) - uz, 0.f) : 0.f);
+            const float gz = zz < cz ? fmaxf(uz - (fz0 - (float)(cz - zz - 1) * H.h) - H.eps, 0.f) : (zz > cz ? fmaxf((fz0 + (float)(zz - cz) * H.h) - uz - H.eps, 0.f) : 0.f);
             for (int yy = max(cy - R, 0); yy <= min(cy + R, H.dy - 1); ++yy) {
-                const float gy = yy < cy ? fmaxf(uy - (fy0 - (float)(cy - yy - 1) * H.h), 0.f) : (yy > cy ? fmaxf((fy0 + (float)(yy - cy) * H.h) - uy, 0.f) : 0.f);
+                const float gy = yy < cy ? fmaxf(uy - (fy0 - (float)(cy - yy - 1) * H.h) - H.eps, 0.f) : (yy > cy ? fmaxf((fy0 + (float)(yy - cy) * H.h) - uy - H.eps, 0.f) : 0.f);
                 // every point of this row of cells is at least sqrt(gy^2 + gz^2) away: skip it when that cannot beat the
                 // current third best (0.998: slack for the rounding of cell faces / binning)
                 const float b3 = __uint_as_float((unsigned)(k3 >> 32));
@@ -323,108 +332,13 @@ three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const 
         if (cy + R < H.dy - 1) bound = fminf(bound, (fy0 + (float)(R + 1) * H.h) - uy);
         if (cz - R > 0) bound = fminf(bound, uz - (fz0 - (float)R * H.h));
         if (cz + R < H.dz - 1) bound = fminf(bound, (fz0 + (float)(R + 1) * H.h) - uz);
-        bound = fmaxf(bound, 0.f);
+        bound = fmaxf(bound - H.eps, 0.f);
         if (__uint_as_float((unsigned)(k3 >> 32)) < bound * bound * 0.998f) break;
     }
     float* od = dist2_all + (cloud * n + pt) * 3;
     int* oi = idx_all + (cloud * n + pt) * 3;
     od[0] = __uint_as_float((unsigned)(k1 >> 32)); od[1] = __uint_as_float((unsigned)(k2 >> 32)); od[2] = __uint_as_float((unsigned)(k3 >> 32));
     oi[0] = (int)(unsigned)k1; oi[1] = (int)(unsigned)k2; oi[2] = (int)(unsigned)k3;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Warp-cooperative form of the same search (EXPERIMENTAL: selected with G4D_NN_COOP=1, not yet validated on the GPU).
-// three_nn_grid_kernel is instruction-bound: 3840 warp instructions per 32 points with 14 of 32 lanes active, because every
-// lane walks its own shells of cells.  Here a warp takes 32 unknown points that are neighbours in the cell-sorted order of
-// `ugrid`, visits the block of cells of the KNOWN grid that covers all of them plus one ring, and stages each run of
-// candidates once in shared memory; every lane then scans the same list (uniform control flow, broadcast reads) keeping its
-// three smallest (d, k) keys -- the same total order, so the same result whatever the visiting order.  A lane is done when its
-// third-best distance is below its distance to the faces of the visited block (same conservative 0.998 margin as above); if
-// any lane is not, the block grows by one ring and only the NEW cells are scanned (every known point is seen exactly once).
-constexpr int NNC_WARPS = 8;
-
-__global__ void __launch_bounds__(NNC_WARPS * 32)
-three_nn_coop_kernel(int n, int m, const float* __restrict__ unknown_all, const float* __restrict__ kgrid_all,
-                     const float* __restrict__ ugrid_all, float* __restrict__ dist2_all, int* __restrict__ idx_all) {
-    __shared__ float4 stage[NNC_WARPS][32];
-    const size_t cloud = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t0 = (blockIdx.x * NNC_WARPS + warp) * 32;
-    if (t0 >= n) return;                                             // warp-uniform
-    const int t = t0 + lane;
-    const bool live = t < n;
-    const float* g = kgrid_all + cloud * grid_cloud_words(m);
-    const GridHdr H = *grid_hdr(g);
-    const int* cell_start = grid_cell_start(g);
-    const float4* sorted = grid_sorted(g);
-    int pt = 0;
-    float ux = 0.f, uy = 0.f, uz = 0.f;
-    int cx = 0, cy = 0, cz = 0;
-    if (live) {
-        pt = __float_as_int(__ldg(&grid_sorted(ugrid_all + cloud * grid_cloud_words(n))[t].w));
-        const float* u = unknown_all + (cloud * n + pt) * 3;
-        ux = __ldg(u); uy = __ldg(u + 1); uz = __ldg(u + 2);
-        cx = cell_coord(ux, H.ox, H.inv_h, H.dx); cy = cell_coord(uy, H.oy, H.inv_h, H.dy); cz = cell_coord(uz, H.oz, H.inv_h, H.dz);
-    }
-    const unsigned FULL = 0xFFFFFFFFu;
-    // block of cells covering the warp's points, plus one ring (lane 0 is always live: t0 < n)
-    int rx0 = max(__reduce_min_sync(FULL, live ? cx : 0x7FFFFFFF) - 1, 0), rx1 = min(__reduce_max_sync(FULL, live ? cx : -1) + 1, H.dx - 1);
-    int ry0 = max(__reduce_min_sync(FULL, live ? cy : 0x7FFFFFFF) - 1, 0), ry1 = min(__reduce_max_sync(FULL, live ? cy : -1) + 1, H.dy - 1);
-    int rz0 = max(__reduce_min_sync(FULL, live ? cz : 0x7FFFFFFF) - 1, 0), rz1 = min(__reduce_max_sync(FULL, live ? cz : -1) + 1, H.dz - 1);
-    int px0 = 0, px1 = -1, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;       // previously visited block: empty
-    const unsigned long long EMPTY = 0x7F80000000000000ull;
-    unsigned long long k1 = EMPTY, k2 = EMPTY, k3 = EMPTY;
-    for (;;) {
-        for (int zz = rz0; zz <= rz1; ++zz)
-            for (int yy = ry0; yy <= ry1; ++yy) {
-                const bool seen_row = zz >= pz0 && zz <= pz1 && yy >= py0 && yy <= py1;      // its cells px0..px1 were visited before
-                const int row = (zz * H.dy + yy) * H.dx;
-                for (int sgm = 0; sgm < (seen_row ? 2 : 1); ++sgm) {
-                    const int xa = !seen_row ? rx0 : (sgm == 0 ? rx0 : px1 + 1);
-                    const int xb = !seen_row ? rx1 : (sgm == 0 ? px0 - 1 : rx1);
-                    if (xa > xb) continue;
-                    const int beg = __ldg(cell_start + row + xa), end = __ldg(cell_start + row + xb + 1);
-                    for (int j0 = beg; j0 < end; j0 += 32) {
-                        const int cnt = min(32, end - j0);
-                        __syncwarp();                                 // the previous batch has been consumed by every lane
-                        if (lane < cnt) stage[warp][lane] = __ldg(sorted + j0 + lane);
-                        __syncwarp();
-                        for (int c = 0; c < cnt; ++c) {
-                            const float4 p = stage[warp][c];          // broadcast read
-                            const unsigned long long key = nn_key(sqdist_ref(ux - p.x, uy - p.y, uz - p.z), __float_as_int(p.w));
-                            if (key < k3) {
-                                k3 = key;
-                                if (k3 < k2) { const unsigned long long tmp = k2; k2 = k3; k3 = tmp; }
-                                if (k2 < k1) { const unsigned long long tmp = k1; k1 = k2; k2 = tmp; }
-                            }
-                        }
-                    }
-                }
-            }
-        const bool whole = rx0 == 0 && ry0 == 0 && rz0 == 0 && rx1 == H.dx - 1 && ry1 == H.dy - 1 && rz1 == H.dz - 1;
-        if (whole) break;
-        // every unvisited known point lies beyond a face of the visited block on a side where the grid continues
-        float bound = INFINITY;
-        if (rx0 > 0) bound = fminf(bound, ux - (H.ox + (float)rx0 * H.h));
-        if (rx1 < H.dx - 1) bound = fminf(bound, (H.ox + (float)(rx1 + 1) * H.h) - ux);
-        if (ry0 > 0) bound = fminf(bound, uy - (H.oy + (float)ry0 * H.h));
-        if (ry1 < H.dy - 1) bound = fminf(bound, (H.oy + (float)(ry1 + 1) * H.h) - uy);
-        if (rz0 > 0) bound = fminf(bound, uz - (H.oz + (float)rz0 * H.h));
-        if (rz1 < H.dz - 1) bound = fminf(bound, (H.oz + (float)(rz1 + 1) * H.h) - uz);
-        bound = fmaxf(bound, 0.f);
-        const bool done = !live || __uint_as_float((unsigned)(k3 >> 32)) < bound * bound * 0.998f;
-        if (__all_sync(FULL, done)) break;
-        px0 = rx0; px1 = rx1; py0 = ry0; py1 = ry1; pz0 = rz0; pz1 = rz1;
-        rx0 = max(rx0 - 1, 0); rx1 = min(rx1 + 1, H.dx - 1);
-        ry0 = max(ry0 - 1, 0); ry1 = min(ry1 + 1, H.dy - 1);
-        rz0 = max(rz0 - 1, 0); rz1 = min(rz1 + 1, H.dz - 1);
-    }
-    if (live) {
-        float* od = dist2_all + (cloud * n + pt) * 3;
-        int* oi = idx_all + (cloud * n + pt) * 3;
-        od[0] = __uint_as_float((unsigned)(k1 >> 32)); od[1] = __uint_as_float((unsigned)(k2 >> 32)); od[2] = __uint_as_float((unsigned)(k3 >> 32));
-        oi[0] = (int)(unsigned)k1; oi[1] = (int)(unsigned)k2; oi[2] = (int)(unsigned)k3;
-    }
 }
 
 }  // namespace g4d
@@ -478,10 +392,6 @@ G4D_API int g4d_three_nn_grid(int b, int n, int m, const float* unknown, const v
     if (b == 0 || n == 0) return 0;
     if (!unknown || !known_grid || !dist2 || !idx) return bad_arg("three_nn_grid: null pointer");
     dim3 gridDim((n + 255) / 256, b);
-    static const bool coop = getenv("G4D_NN_COOP") && atoi(getenv("G4D_NN_COOP")) == 1;      // experimental, off by default
-    if (coop && unknown_grid && m > 0)
-        three_nn_coop_kernel<<<gridDim, NNC_WARPS * 32, 0, (cudaStream_t)stream>>>(n, m, unknown, (const float*)known_grid, (const float*)unknown_grid, dist2, idx);
-    else
-        three_nn_grid_kernel<<<gridDim, 256, 0, (cudaStream_t)stream>>>(n, m, unknown, (const float*)known_grid, (const float*)unknown_grid, dist2, idx);
+    three_nn_grid_kernel<<<gridDim, 256, 0, (cudaStream_t)stream>>>(n, m, unknown, (const float*)known_grid, (const float*)unknown_grid, dist2, idx);
     return finish_launch("g4d three_nn_grid");
 }

@@ -67,7 +67,7 @@ def pack_fp_head(fp_mlp, fc_layer, device):
 
 def fp_interp_mlp(packed, unknown, known, known_feats):
     """unknown (B,n,3), known (B,m,3), known_feats (B,C,m) fp32 -> (features (B,c2,n) fp32, logits (B,n,h2) fp32)."""
-    from .pointnet2_utils import three_nn_raw
+    from .pointnet2_utils import three_nn_raw, point_major_of
     unknown = unknown if unknown.is_contiguous() else unknown.contiguous()
     known = known if known.is_contiguous() else known.contiguous()
     B, n, _ = unknown.shape
@@ -75,9 +75,8 @@ def fp_interp_mlp(packed, unknown, known, known_feats):
     dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
     idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
     three_nn_raw(unknown, known, dist2, idx)
-    known_pm = getattr(known_feats, "_g4d_pm", None)       # emitted by the producing FP level's epilogue (g4d_bias_relu_pm)
-    if (known_pm is None or known_pm.dtype != torch.float16 or tuple(known_pm.shape) != (B, m, known_feats.shape[1])
-            or not known_pm.is_contiguous()):
+    known_pm = point_major_of(known_feats)       # emitted by the producing FP level's epilogue; None when stale
+    if known_pm is None:
         known_pm = known_feats.detach().transpose(1, 2).to(torch.float16).contiguous()
     feat = torch.empty(B, packed.c2, n, dtype=torch.float32, device=unknown.device)
     logits = torch.empty(B, n, packed.h2, dtype=torch.float32, device=unknown.device)

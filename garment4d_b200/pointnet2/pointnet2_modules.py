@@ -28,14 +28,13 @@ from . import pytorch_utils as pt_utils
 # Feature-propagation MLPs in eval mode: "half" = one fp16 library GEMM per layer over the whole batch (default),
 # "conv" = per-cloud fp32/TF32 library convolution.  Both with our prologue / bias+ReLU epilogue kernels.
 _FP_GEMM = os.environ.get("G4D_FP_GEMM", "half")
-_FP_LT_EPILOGUE = os.environ.get("G4D_FP_LT_EPILOGUE", "0") == "1"
 
 
 def _as_point_major_half(features: torch.Tensor) -> torch.Tensor:
     """(B,C,N) fp32 channel-major -> (B,N,C) fp16 point-major, the gather layout of the fused kernel.
     A fused SA module attaches this copy to its output as ``_g4d_pm`` so the next level does not recompute it."""
-    pm = getattr(features, "_g4d_pm", None)
-    if pm is not None and pm.shape[0] == features.shape[0] and pm.shape[1] == features.shape[2] and pm.shape[2] == features.shape[1]:
+    pm = pointnet2_utils.point_major_of(features)     # trusted only while `features` is unmodified (version counter)
+    if pm is not None:
         return pm
     return features.detach().transpose(1, 2).to(torch.float16).contiguous()
 
@@ -141,7 +140,7 @@ class _PointnetSAModuleBase(nn.Module):
                                   _lib.stream_ptr())
             _lib.check(rc, "g4d_sa_mlp_max")
             off += br.c_out
-        out_cm._g4d_pm = out_pm
+        pointnet2_utils.attach_point_major(out_cm, out_pm)
         return new_xyz, out_cm
 
     # ---- public forward ----------------------------------------------------------------------------------
@@ -230,8 +229,8 @@ class PointnetFPModule(nn.Module):
                 # written fp16 in (C, B*n) layout, hidden layers stay fp16 (fp32 accumulation; same 11-bit operand precision
                 # as the TF32 convolutions torch runs by default), bias+ReLU passes are ours, the last layer's GEMM returns
                 # fp32 and its epilogue writes the reference layout (B, C, n) (+ the fp16 point-major copy for the next level).
-                kpm = getattr(known_feats, "_g4d_pm", None)      # fp16 point-major copy emitted by the producing level
-                spm = None if unknow_feats is None else getattr(unknow_feats, "_g4d_pm", None)
+                kpm = pointnet2_utils.point_major_of(known_feats)      # fp16 point-major copy emitted by the producing level
+                spm = None if unknow_feats is None else pointnet2_utils.point_major_of(unknow_feats)
                 pm_ok = lambda t, shape: (t is not None and t.dtype == torch.float16 and tuple(t.shape) == shape and t.is_contiguous())
                 layers = folded["half"]
                 if (pm_ok(kpm, (B, m, c2)) and (c1 == 0 or pm_ok(spm, (B, n, c1))) and c2 % 8 == 0 and c1 % 8 == 0
@@ -243,10 +242,6 @@ class PointnetFPModule(nn.Module):
                     _lib.check(rc, "g4d_fp_interp_concat_rows_h")
                     for li, (w16, b) in enumerate(layers):
                         if li < len(layers) - 1:
-                            if _FP_LT_EPILOGUE:
-                                # EXPERIMENTAL (G4D_FP_LT_EPILOGUE=1, not yet measured): bias + ReLU in the library GEMM's epilogue
-                                x = torch._addmm_activation(b.to(torch.float16), x, w16.t(), use_gelu=False)
-                                continue
                             x = F.linear(x, w16)
                             rc = L.g4d_bias_relu_rows_h(B * n, w16.shape[0], _lib.ptr(x), _lib.ptr(b), 1, _lib.stream_ptr())
                             _lib.check(rc, "g4d_bias_relu_rows_h")
@@ -258,7 +253,7 @@ class PointnetFPModule(nn.Module):
                                                              _lib.stream_ptr())
                             _lib.check(rc, "g4d_bias_relu_rows_unpack")
                             if pm is not None:
-                                out._g4d_pm = pm
+                                pointnet2_utils.attach_point_major(out, pm)
                     return out
                 x = torch.empty(c2 + c1, B * n, dtype=torch.float16, device=dev)
                 if (kpm is not None and c2 % 8 == 0 and kpm.dtype == torch.float16 and tuple(kpm.shape) == (B, m, c2)
@@ -282,7 +277,7 @@ class PointnetFPModule(nn.Module):
                                                     _lib.stream_ptr())
                         _lib.check(rc, "g4d_bias_relu_unpack")
                         if pm is not None:
-                            out._g4d_pm = pm
+                            pointnet2_utils.attach_point_major(out, pm)
                 return out
             new_features = torch.empty(B, c2 + c1, n, dtype=torch.float32, device=dev)
             rc = L.g4d_fp_interp_concat(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(known_feats), _lib.ptr(skip),
@@ -314,7 +309,7 @@ class PointnetFPModule(nn.Module):
                     pm = torch.empty(y.shape[0], y.shape[2], y.shape[1], dtype=torch.float16, device=y.device)
                     rc = L.g4d_bias_relu_pm(y.shape[0], y.shape[1], y.shape[2], _lib.ptr(y), _lib.ptr(b), 1, _lib.ptr(pm), _lib.stream_ptr())
                     _lib.check(rc, "g4d_bias_relu_pm")
-                    y._g4d_pm = pm
+                    pointnet2_utils.attach_point_major(y, pm)
                 elif y.shape[0] * y.shape[1] <= 65535 and y.is_contiguous():
                     rc = L.g4d_bias_relu_inplace(y.shape[0], y.shape[1], y.shape[2], _lib.ptr(y), _lib.ptr(b), 1, _lib.stream_ptr())
                     _lib.check(rc, "g4d_bias_relu_inplace")

@@ -34,6 +34,46 @@ def _f32(*shape, device):
     return torch.empty(*shape, dtype=torch.float32, device=device)
 
 
+def attach_point_major(features: torch.Tensor, pm: torch.Tensor) -> None:
+    """Remembers the fp16 point-major copy ``pm (B,N,C)`` of ``features (B,C,N)`` on the tensor, together with the tensor's
+    version counter: the copy is only trusted while `features` has not been modified in place (see point_major_of)."""
+    try:
+        features._g4d_pm = (pm, features._version)
+    except Exception:
+        pass
+
+
+def point_major_of(features: torch.Tensor):
+    """The fp16 point-major copy attached by attach_point_major, or None when there is none or it is stale: `features`
+    was written in place since (version counter), or shape / dtype / device no longer match."""
+    hit = getattr(features, "_g4d_pm", None)
+    if not isinstance(hit, tuple) or len(hit) != 2:
+        return None
+    pm, ver = hit
+    B, C, N = features.shape
+    if (ver != features._version or pm.dtype != torch.float16 or pm.device != features.device or tuple(pm.shape) != (B, N, C)
+            or not pm.is_contiguous()):
+        try:
+            del features._g4d_pm
+        except Exception:
+            pass
+        return None
+    return pm
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    """The checks the compiled-module mirror applies (garment4d_b200/pointnet2_cuda.py) for tensors whose pointers go
+    straight to the C ABI on the grid / fused routes: CUDA, exact dtype, contiguous.  The reference raises on a dtype
+    mismatch too (``tensor.data<float>()``)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return t
+
+
 GRID_MIN_POINTS = 2048     # below this the brute-force scans are already cheap
 FPS_PRUNE_MIN_POINTS = 2048
 
@@ -160,6 +200,8 @@ def three_nn_raw(unknown, known, dist2, idx):
     B, N, _ = unknown.size()
     m = known.size(1)
     if N >= GRID_MIN_POINTS and 512 <= m <= (1 << 20):
+        _chk(unknown, torch.float32, "unknown"); _chk(known, torch.float32, "known")
+        _chk(dist2, torch.float32, "dist2"); _chk(idx, torch.int32, "idx")
         kgrid = build_grid(known, -max(4.0, round(0.7 * float(m) ** 0.5)))
         ugrid = _cached_grid(unknown)      # only a processing order: any grid over `unknown` will do
         rc = _lib.lib().g4d_three_nn_grid(B, N, m, _lib.ptr(unknown), _lib.ptr(kgrid), _lib.ptr(ugrid), _lib.ptr(dist2),
@@ -230,6 +272,7 @@ class BallQuery(Function):
         npoint = new_xyz.size(1)
         idx = torch.zeros(B, npoint, nsample, dtype=torch.int32, device=xyz.device)
         if GRID_MIN_POINTS <= N <= 65536:
+            _chk(xyz, torch.float32, "xyz"); _chk(new_xyz, torch.float32, "new_xyz")
             grid = _cached_grid(xyz, radius)
             if grid is None:
                 grid = build_grid(xyz, radius)
@@ -251,7 +294,7 @@ ball_query = BallQuery.apply
 
 def ball_query_pair(radius0, nsample0, radius1, nsample1, xyz, new_xyz):
     """Both scales of an MSG module from one scan of the cloud (g4d_ball_query2); each result equals ball_query's."""
-    assert xyz.is_contiguous() and new_xyz.is_contiguous()
+    _chk(xyz, torch.float32, "xyz"); _chk(new_xyz, torch.float32, "new_xyz")
     B, N, _ = xyz.size()
     P = new_xyz.size(1)
     idx0 = torch.zeros(B, P, nsample0, dtype=torch.int32, device=xyz.device)
@@ -281,6 +324,9 @@ class _QueryAndGroupFused(Function):
 
     @staticmethod
     def forward(ctx, radius, nsample, use_xyz, xyz, new_xyz, features):
+        _chk(xyz, torch.float32, "xyz"); _chk(new_xyz, torch.float32, "new_xyz")
+        if features is not None:
+            _chk(features, torch.float32, "features")
         B, N, _ = xyz.size()
         P = new_xyz.size(1)
         C = 0 if features is None else features.size(1)
@@ -333,8 +379,8 @@ class QueryAndGroup(nn.Module):
         """xyz (B,N,3), new_xyz (B,npoint,3), features (B,C,N) or None -> (B, 3+C, npoint, nsample)"""
         if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-        if self.nsample in _FUSED_NSAMPLE and xyz.is_contiguous() and new_xyz.is_contiguous() and (
-                features is None or features.is_contiguous()):
+        f32cuda = lambda t: t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        if self.nsample in _FUSED_NSAMPLE and f32cuda(xyz) and f32cuda(new_xyz) and (features is None or f32cuda(features)):
             return _QueryAndGroupFused.apply(self.radius, self.nsample, self.use_xyz, xyz, new_xyz, features)
         # generic composition, operator by operator (pointnet2_utils.py:250-265)
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)

@@ -5,8 +5,6 @@ CUDA stream: the host->device copy of chunk i+1, the kernels of chunk i and the 
 and the latency-bound kernels of different chunks (FPS is a serial chain per cloud, the grouped MLP hands off between
 warps) fill each other's idle SMs.  Results are identical to one big call: every kernel works per cloud.
 """
-import os
-
 import torch
 
 from . import _lib
@@ -22,18 +20,7 @@ class EncoderLBSRunner:
         self.smpl = smpl
         self.chunks = max(1, int(chunks))
         self.device = device if device is not None else next(model.parameters()).device
-        # EXPERIMENTAL (G4D_CHUNK_PRIORITY=1, off by default): earlier frame groups on higher-priority streams, so that the
-        # block scheduler finishes group k's kernels before it starts group k+1's instead of interleaving all groups' FPS
-        if os.environ.get("G4D_CHUNK_PRIORITY", "0") == "1":
-            lo, hi = -1, 0
-            try:
-                hi, lo = torch.cuda.Stream.priority_range()      # (least, greatest) = (0, -5) on current devices
-            except Exception:
-                pass
-            prios = [max(lo, min(hi, lo + i)) for i in range(self.chunks)]
-            self.streams = [torch.cuda.Stream(device=self.device, priority=p) for p in prios]
-        else:
-            self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.chunks)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.chunks)]
         self.lbs_stream = torch.cuda.Stream(device=self.device)    # lbs() does not depend on the encoder: its own stream
 
     def _bounds(self, C):

@@ -169,15 +169,33 @@ _WORKER = r'''
 import os, sys, json
 sys.path.insert(0, os.environ["G4D_ROOT"])
 import numpy as np, torch, torch.distributed as dist
-from garment4d_b200.sharding import shard_sequences, max_over_ranks
+from garment4d_b200.sharding import shard_sequences, max_over_ranks, FlatGradientReducer, allreduce_flat_gradients
 dist.init_process_group("gloo")
 r, w = dist.get_rank(), dist.get_world_size()
-lo, hi = shard_sequences(7, r, w)
+mine = shard_sequences(7, r, w)
 t = max_over_ranks(float(10 + r))
-own = torch.zeros(7, dtype=torch.int64); own[lo:hi] = 1
+own = torch.zeros(7, dtype=torch.int64)
+for i in mine: own[i] += 1
 dist.all_reduce(own)
+# flat gradient all-reduce: rank 1 leaves one parameter without a gradient (it must still take part, as zeros)
+torch.manual_seed(0)
+lin = torch.nn.Linear(4, 3); extra = torch.nn.Parameter(torch.ones(5))
+params = list(lin.parameters()) + [extra]
+red = FlatGradientReducer(params)
+x = torch.full((2, 4), float(r + 1))
+loss = lin(x).sum() + (extra.sum() * 3.0 if r == 0 else 0.0)
+loss.backward()
+red.all_reduce()
+g_w = lin.weight.grad.clone(); g_e = extra.grad.clone()
+# one-shot helper, same result
+lin2 = torch.nn.Linear(4, 3); lin2.load_state_dict(lin.state_dict()); extra2 = torch.nn.Parameter(torch.ones(5))
+loss2 = lin2(x).sum() + (extra2.sum() * 3.0 if r == 0 else 0.0)
+loss2.backward()
+allreduce_flat_gradients(list(lin2.parameters()) + [extra2])
+same = bool(torch.equal(lin2.weight.grad, g_w) and torch.equal(extra2.grad, g_e))
 if r == 0:
-    print(json.dumps({"cover": own.tolist(), "tmax": t, "lo_hi": [lo, hi]}))
+    print(json.dumps({"cover": own.tolist(), "tmax": t, "mine": mine, "gw": g_w[0].tolist(), "ge": g_e.tolist(), "same": same,
+                      "nbytes": red.nbytes}))
 dist.destroy_process_group()
 '''
 
@@ -191,9 +209,27 @@ def test_sharding_world2_gloo(tmp_path):
     assert out.returncode == 0, out.stderr[-3000:]
     import json
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-    assert res["cover"] == [1] * 7            # every sequence owned by exactly one rank
+    # the reference sampler's partition (utils/train_utils.py:12-31): strided, padded by wrap-around to equal shards
+    assert res["mine"] == [0, 2, 4, 6]
+    assert res["cover"] == [2, 1, 1, 1, 1, 1, 1]          # 7 sequences on 2 ranks: 4 + 4, sequence 0 owned twice (the padding)
     assert res["tmax"] == 11.0                # max over ranks, as bench.py reports
-    assert res["lo_hi"] == [0, 4]
+    # d(sum(lin(x)))/dW = column sums of x = 2*(r+1) per entry -> mean over ranks (2 + 4) / 2 = 3; extra: (3 + 0) / 2
+    assert res["gw"] == [3.0] * 4 and res["ge"] == [1.5] * 5 and res["same"]
+    assert res["nbytes"] == 4 * (12 + 3 + 5)
+
+
+def test_shard_sequences_matches_the_reference_sampler():
+    from garment4d_b200.sharding import shard_sequences
+    for n, w in ((32, 8), (32, 4), (7, 2), (5, 8), (1, 4), (0, 2)):
+        shards = [shard_sequences(n, r, w) for r in range(w)]
+        per = -(-n // w) if n else 0
+        assert all(len(s) == per for s in shards)
+        total = per * w
+        idx = list(range(n))
+        while n and len(idx) < total:
+            idx += idx[: total - len(idx)]
+        assert shards == [idx[r:total:w] for r in range(w)]
+        assert set(i for s in shards for i in s) == set(range(n))
 
 
 def test_bench_reads_ncu_traffic_from_committed_profiles():

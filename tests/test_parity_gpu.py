@@ -201,7 +201,7 @@ def _brute_nn(u, k):
     return d2, idx
 
 
-@pytest.mark.parametrize("shape", ["body", "cube", "coincident", "outlier", "line", "planar_dups"])
+@pytest.mark.parametrize("shape", ["body", "cube", "coincident", "outlier", "line", "planar_dups", "far_origin", "far_origin_big", "needle"])
 def test_grid_searches_equal_brute_force(cuda, shape):
     """The uniform-grid ball query / three_nn must reproduce the brute-force kernels bit for bit on awkward clouds."""
     B, N, m = 2, 4096, 600
@@ -217,6 +217,15 @@ def test_grid_searches_equal_brute_force(cuda, shape):
     elif shape == "line":
         xyz = np.zeros((B, N, 3), np.float32)
         xyz[..., 0] = rs.rand(B, N).astype(np.float32)
+    elif shape == "far_origin":
+        # far from the origin relative to the radii (|coord| ~ 1e3 = 20000 r for r = 0.05): coordinates are coarse (ulp 6e-5),
+        # cell faces and binning round -- the grid searches must still see every hit the brute-force scan sees
+        xyz = (clouds(63, B, N, "body", dup_frac=0.1) + np.array([1000.0, -2000.0, 512.0], np.float32)).astype(np.float32)
+    elif shape == "far_origin_big":
+        xyz = (clouds(64, B, N, "cube", dup_frac=0.1) + np.array([65536.0, 0.0, -30000.0], np.float32)).astype(np.float32)
+    elif shape == "needle":
+        # extremely elongated: thousands of cells along one axis would be needed for cell edge = radius
+        xyz = (rs.rand(B, N, 3) * np.array([400.0, 0.05, 0.05])).astype(np.float32)
     else:
         xyz = np.zeros((B, N, 3), np.float32)
         xyz[..., :2] = (rs.randint(0, 40, (B, N, 2)) * 0.025).astype(np.float32)     # lattice: many exact distance ties

@@ -56,7 +56,7 @@ def test_fused_sa_module_vs_torch(cuda, spec):
     feats = torch.randn(B, cin, N, device=cuda) if cin else None
     with torch.no_grad():
         new_xyz, out = mod(xyz, feats)                       # fused route
-        assert getattr(out, "_g4d_pm", None) is not None, "fused route was not taken"
+        assert pu.point_major_of(out) is not None, "fused route was not taken"
         mod.fused = False
         old = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = False              # true fp32 reference
@@ -68,7 +68,7 @@ def test_fused_sa_module_vs_torch(cuda, spec):
     assert torch.equal(new_xyz, ref_xyz)
     assert out.shape == ref.shape
     _close(out, ref)
-    _close(out._g4d_pm.float().transpose(1, 2), ref)
+    _close(pu.point_major_of(out).float().transpose(1, 2), ref)
 
 
 def test_fused_route_tracks_weight_updates(cuda):
@@ -92,7 +92,7 @@ def test_training_mode_uses_operator_route_and_backprops(cuda):
     xyz = torch.from_numpy(clouds(9, 2, 256, "cube")).to(cuda)
     feats = torch.randn(2, 4, 256, device=cuda, requires_grad=True)
     _, out = mod(xyz, feats)
-    assert getattr(out, "_g4d_pm", None) is None
+    assert pu.point_major_of(out) is None
     out.sum().backward()
     assert feats.grad is not None and torch.isfinite(feats.grad).all()
     assert all(p.grad is not None for p in mod.parameters())
@@ -155,9 +155,9 @@ def test_fp_module_eval_routes_vs_operator_sequence(cuda, spec):
             kin = kf.clone()
             sin = None if skip is None else skip.clone()
             if route == "half+pm" and c2 % 8 == 0:      # features with the fp16 point-major copies the fused levels attach
-                kin._g4d_pm = kin.transpose(1, 2).to(torch.float16).contiguous()
+                pu.attach_point_major(kin, kin.transpose(1, 2).to(torch.float16).contiguous())
                 if sin is not None:
-                    sin._g4d_pm = sin.transpose(1, 2).to(torch.float16).contiguous()       # -> the point-major rows route
+                    pu.attach_point_major(sin, sin.transpose(1, 2).to(torch.float16).contiguous())       # -> the point-major rows route
             try:
                 out = mod(unknown, known, sin, kin)
             finally:
