@@ -55,7 +55,7 @@ class _FusedBranch:
         blob = torch.empty(nbytes, dtype=torch.uint8)
         rc = L.g4d_sa_mlp_pack_params(ctypes.byref(self.desc), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                                       w3.data_ptr(), b3.data_ptr(), blob.data_ptr())
-        _lib.check(rc, "g4d_sa_mlp_pack_params")
+        _lib.check(rc, "g4d_sa_mlp_pack_params")        # raises when a folded weight / bias does not fit fp16
         self.params = blob.to(device)
         self.c_out = w3.shape[0]
 
@@ -105,7 +105,12 @@ class _PointnetSAModuleBase(nn.Module):
         if hit is None or hit[0] != ver:
             br = None
             if fused_branch_supported(self.mlps[i], self.groupers[i], c_in):
-                br = _FusedBranch(self.mlps[i], self.groupers[i].nsample, c_in, device)
+                try:
+                    br = _FusedBranch(self.mlps[i], self.groupers[i].nsample, c_in, device)
+                except _lib.G4DError as e:
+                    if "fp16 range" not in str(e):
+                        raise
+                    br = None       # fp16 operands cannot hold these folded weights: operator route (fp32 / TF32 layers)
             hit = (ver, br)
             self._fused_cache[key] = hit
         return hit[1]
@@ -319,9 +324,10 @@ class PointnetFPModule(nn.Module):
         return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
 
     emit_point_major = False      # set by the encoder on the level that feeds the fused finest-level kernel
+    fused = True                  # set False to force the reference's operator sequence (three_nn, three_interpolate, cat, SharedMLP)
 
     def _folded_mlp(self, x, skip=None):
-        if self.training or not x.is_cuda or (torch.is_grad_enabled() and (x.requires_grad or (skip is not None and skip.requires_grad)
+        if not self.fused or self.training or not x.is_cuda or (torch.is_grad_enabled() and (x.requires_grad or (skip is not None and skip.requires_grad)
                                                                            or any(p.requires_grad for p in self.mlp.parameters()))):
             return None
         ver = pt_utils.shared_mlp_version(self.mlp)

@@ -123,11 +123,13 @@ typedef struct g4d_sa_mlp_desc {
     int k0;            /* padded input width of layer 1 in fp16 elements (from g4d_sa_mlp_k0)       */
 } g4d_sa_mlp_desc;
 
-/* Padded layer-1 K for a given c_in (9 split-precision xyz slots + c_in, rounded up to 16). */
+/* Padded layer-1 K for a given c_in (c_in + 9 split-precision xyz slots + 2 bias slots, rounded up to 16). */
 int g4d_sa_mlp_k0(int c_in);
-/* Bytes of the packed parameter blob (fp16 UMMA-canonical weights + fp32 biases) for a descriptor. */
+/* Bytes of the packed parameter blob (fp16 UMMA-canonical weights with the layer-1/2 biases folded in as extra K
+ * positions, fp32 layer-3 biases, one constant operand) for a descriptor. */
 size_t g4d_sa_mlp_param_bytes(const g4d_sa_mlp_desc* d);
-/* Packs host fp32 folded weights w1 (c1, 3+c_in), w2 (c2,c1), w3 (c3,c2) and biases into `blob` (host memory). */
+/* Packs host fp32 folded weights w1 (c1, 3+c_in), w2 (c2,c1), w3 (c3,c2) and biases into `blob` (host memory).
+ * Fails (cudaErrorInvalidValue, "fp16 range") when a value does not fit fp16: take the operator route then. */
 int g4d_sa_mlp_pack_params(const g4d_sa_mlp_desc* d, const float* w1, const float* b1, const float* w2, const float* b2,
                            const float* w3, const float* b3, void* blob);
 /* xyz (b,n,3), new_xyz (b,m,3), idx (b,m,nsample), feat_pm: point-major fp16 features (b,n,c_in) or NULL.
@@ -137,9 +139,6 @@ int g4d_sa_mlp_pack_params(const g4d_sa_mlp_desc* d, const float* w1, const floa
 int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int b, int n, int m, const float* xyz,
                    const float* new_xyz, const int* idx, const void* feat_pm, float* out_cm, void* out_pm,
                    int out_c_total, int out_c_off, void* stream);
-
-/* debug aid: clock64() timeline of CTA 0 of the following g4d_sa_mlp_max launches (buf: >= 400 int64 on the device; NULL = off) */
-void g4d_debug_timeline(void* buf);
 
 /* Fused feature propagation (no skip features) + optional segmentation head on tcgen05: inverse-distance weights
  * from three_nn's squared distances, 3-tap interpolation, the FP module's 2-layer 1x1-conv MLP (eval BN folded, ReLU)

@@ -35,6 +35,8 @@ def lib():
         L.orc_opt_n_threads.argtypes = [_c]
         L.orc_opt_n_threads.restype = _c
         L.orc_num_threads.restype = _c
+        L.orc_set_num_threads.argtypes = [_c]
+        L.orc_set_num_threads.restype = None
         for name, args in {
             "orc_furthest_point_sampling": [_c, _c, _c, _f, _f, _i],
             "orc_furthest_point_sampling_fast": [_c, _c, _c, _f, _f, _i],
@@ -74,6 +76,10 @@ def _i32(a):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
 
 
 def opt_n_threads(n):

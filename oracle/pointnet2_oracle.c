@@ -41,6 +41,11 @@ int orc_opt_n_threads(int work_size) {
     return v;
 }
 
+/* bench.py's reference arm sets the thread count explicitly (torchrun exports OMP_NUM_THREADS=1 to every rank). */
+void orc_set_num_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

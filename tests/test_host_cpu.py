@@ -38,7 +38,7 @@ def test_library_is_sm100a_native_and_has_tcgen05():
     from garment4d_b200 import _lib
     out = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3g4d17sa_mlp_max_kernelILi32ELb1ELi1EEEvNS_9SaMlpArgsE",
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3g4d17sa_mlp_max_kernelILi32ELb1ELb1EEEvNS_9SaMlpArgsE",
                            _lib.SO_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass, "grouped-MLP kernel is not on the tcgen05 path"
 
@@ -122,7 +122,9 @@ def test_fold_shared_mlp_equals_conv_bn_relu_on_cpu():
 
 
 def test_sa_mlp_param_packing_layout():
-    """g4d_sa_mlp_pack_params (host function, no GPU): UMMA canonical K-major image + hi/lo split of the xyz columns."""
+    """g4d_sa_mlp_pack_params (host function, no GPU): UMMA canonical K-major images; hi/lo split of the xyz columns; the
+    layer-1 bias in the two spare K positions behind them (they meet the constant 1.0 the producers write), the layer-2
+    bias as one extra K-slice of W2 (it meets the constant ones operand), b3 in fp32; the fp16 range guard."""
     from garment4d_b200 import _lib
     L = _lib.lib()
     c_in, c1, c2, c3, K = 16, 32, 16, 40, 16
@@ -130,25 +132,56 @@ def test_sa_mlp_param_packing_layout():
     assert d.k0 == 32
     nbytes = L.g4d_sa_mlp_param_bytes(ctypes.byref(d))
     c3p = 128
-    assert nbytes == 2 * (d.k0 * c1 + c1 * c2 + c2 * c3p) + 4 * (c1 + c2 + c3p)
+    assert nbytes == 2 * (d.k0 * c1 + (c1 + 16) * c2 + c2 * c3p) + 4 * c3p + 128 * 16 * 2
     rs = np.random.RandomState(0)
     w1, w2, w3 = (rs.randn(c1, 3 + c_in).astype(np.float32), rs.randn(c2, c1).astype(np.float32), rs.randn(c3, c2).astype(np.float32))
     b1, b2, b3 = (rs.randn(c).astype(np.float32) for c in (c1, c2, c3))
     blob = np.zeros(nbytes, np.uint8)
     rc = L.g4d_sa_mlp_pack_params(ctypes.byref(d), *(a.ctypes.data for a in (w1, b1, w2, b2, w3, b3)), blob.ctypes.data)
     assert rc == 0
-    W1 = blob[:2 * d.k0 * c1].view(np.float16).reshape(d.k0 // 8, c1, 8)          # [k/8][row][k%8]
-    W1 = W1.transpose(1, 0, 2).reshape(c1, d.k0).astype(np.float32)                 # (row, k)
-    assert np.array_equal(W1[:, :c_in], w1[:, 3:].astype(np.float16).astype(np.float32))       # features first
-    wh = w1[:, :3].astype(np.float16).astype(np.float32)
+
+    def canon(off, rows, k):                                     # [k/8][row][k%8] fp16 -> (row, k) fp32
+        img = blob[off:off + 2 * rows * k].view(np.float16).reshape(k // 8, rows, 8)
+        return img.transpose(1, 0, 2).reshape(rows, k).astype(np.float32), off + 2 * rows * k
+
+    h = lambda a: a.astype(np.float16).astype(np.float32)
+    W1, o = canon(0, c1, d.k0)
+    assert np.array_equal(W1[:, :c_in], h(w1[:, 3:]))                                            # features first
+    wh = h(w1[:, :3])
     assert np.array_equal(W1[:, c_in:c_in + 3], wh) and np.array_equal(W1[:, c_in + 3:c_in + 6], wh)
     assert np.allclose(W1[:, c_in + 6:c_in + 9], w1[:, :3] - wh, atol=1e-6)
     assert np.abs(W1[:, c_in:c_in + 3] + W1[:, c_in + 6:c_in + 9] - w1[:, :3]).max() < 2e-6     # hi + lo recovers fp32 weights
-    assert not W1[:, c_in + 9:].any()
-    off = 2 * (d.k0 * c1 + c1 * c2 + c2 * c3p)
-    assert np.array_equal(blob[off:off + 4 * c1].view(np.float32), b1)
+    assert np.array_equal(W1[:, c_in + 9], h(b1)) and np.abs(W1[:, c_in + 9] + W1[:, c_in + 10] - b1).max() < 2e-6
+    assert not W1[:, c_in + 11:].any()
+    W2, o = canon(o, c2, c1 + 16)
+    assert np.array_equal(W2[:, :c1], h(w2))
+    assert np.array_equal(W2[:, c1], h(b2)) and np.abs(W2[:, c1] + W2[:, c1 + 1] - b2).max() < 2e-6 and not W2[:, c1 + 2:].any()
+    W3, o = canon(o, c3p, c2)
+    assert np.array_equal(W3[:c3], h(w3)) and not W3[c3:].any()
+    assert np.array_equal(blob[o:o + 4 * c3].view(np.float32), b3)
+    o += 4 * c3p
+    ones, o = canon(o, 128, 16)
+    assert (ones[:, :2] == 1).all() and not ones[:, 2:].any() and o == nbytes
     bad = _lib.SaMlpDesc(c_in, 20, c2, c3, K, d.k0)
     assert L.g4d_sa_mlp_param_bytes(ctypes.byref(bad)) == 0 and b"multiples of 16" in L.g4d_last_error()
+    # a folded weight or bias outside the fp16 range is refused (the caller then takes the operator route)
+    w2_big = w2.copy(); w2_big[3, 5] = 7.0e4
+    assert L.g4d_sa_mlp_pack_params(ctypes.byref(d), *(a.ctypes.data for a in (w1, b1, w2_big, b2, w3, b3)), blob.ctypes.data) != 0
+    assert b"fp16 range" in L.g4d_last_error()
+    b1_big = b1.copy(); b1_big[0] = -1.0e5
+    assert L.g4d_sa_mlp_pack_params(ctypes.byref(d), *(a.ctypes.data for a in (w1, b1_big, w2, b2, w3, b3)), blob.ctypes.data) != 0
+
+
+def test_sa_route_falls_back_when_folded_weights_leave_fp16_range():
+    """BatchNorm statistics that push a folded weight past 65504: the fused branch is refused, the module takes the operator route."""
+    import torch
+    from garment4d_b200.pointnet2 import pointnet2_modules as pm
+    sa = pm.PointnetSAModuleMSG(npoint=16, radii=[0.2], nsamples=[16], mlps=[[0, 16, 16, 32]]).eval()
+    assert sa._branch(0, 0, "cpu") is not None
+    with torch.no_grad():
+        sa.mlps[0].layer1.bn.bn.running_var.fill_(1e-12)          # scale = gamma / sqrt(var + eps) ~ 316 ... not enough alone
+        sa.mlps[0].layer1.bn.bn.weight.fill_(1e4)                 # ... times gamma = 1e4 -> folded weights ~ 3e6 * w
+    assert sa._branch(0, 0, "cpu") is None
 
 
 def test_bench_reference_arm_prints_contract_line():
