@@ -46,12 +46,15 @@ _SIGNATURES = {
     "g4d_grid_bytes": (_sz, [_i, _i]),
     "g4d_grid_build": (_i, [_i, _i, _vp, _f, _vp, _vp]),
     "g4d_fps_gather_grid": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "g4d_fps_workspace_bytes": (_sz, [_i, _i]),
+    "g4d_fps_gather_ws": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4d_ball_query2_grid": (_i, [_i, _i, _i, _f, _i, _vp, _f, _i, _vp, _vp, _vp, _vp]),
     "g4d_three_nn_grid": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_sa_mlp_k0": (_i, [_i]),
     "g4d_sa_mlp_param_bytes": (_sz, [ctypes.POINTER(SaMlpDesc)]),
     "g4d_sa_mlp_pack_params": (_i, [ctypes.POINTER(SaMlpDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_sa_mlp_max": (_i, [ctypes.POINTER(SaMlpDesc), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "g4d_debug_timeline": (None, [_vp]),
     "g4d_debug_fp_counters": (None, [_vp]),
     "g4d_fp_param_bytes": (_sz, [ctypes.POINTER(FpDesc)]),
     "g4d_fp_pack_params": (_i, [ctypes.POINTER(FpDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -24,7 +24,7 @@ namespace g4d {
 
 template <int T, int PPT>
 __global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
-fps_pruned_kernel(int n, int m, int lg_bs, const float* __restrict__ grid_all, int* __restrict__ idx_all,
+fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all, long long cloud_stride, int* __restrict__ idx_all,
                   float* __restrict__ new_xyz_all) {
     extern __shared__ __align__(16) float soa[];           // xs[PPT][T], ys[PPT][T], zs[PPT][T]
     float* xs = soa;
@@ -38,7 +38,7 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float* __restrict__ grid_all, i
     __shared__ float first_xyz[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t cloud = blockIdx.x;
-    const float4* sorted = grid_sorted(grid_all + cloud * grid_cloud_words(n));
+    const float4* sorted = sorted_all + cloud * cloud_stride;      // any spatially coherent order of the cloud: (x, y, z, bits(k))
     int* idx_out = idx_all + cloud * (size_t)m;
     float* new_xyz = new_xyz_all ? new_xyz_all + cloud * (size_t)m * 3 : nullptr;
     const unsigned himask = lg_bs ? ~((1u << (32 - lg_bs)) - 1u) : 0u;
@@ -179,14 +179,31 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float* __restrict__ grid_all, i
 }
 
 template <int T, int PPT>
-static int launch_fps_pruned(int b, int n, int m, int lg, const float* grid, int* idx, float* new_xyz, cudaStream_t s) {
+static int launch_fps_pruned(int b, int n, int m, int lg, const float4* sorted, long long stride, int* idx, float* new_xyz, cudaStream_t s) {
     auto kern = fps_pruned_kernel<T, PPT>;
     size_t smem = (size_t)T * PPT * (3 * sizeof(float) + sizeof(unsigned short));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("fps_pruned: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    kern<<<b, T, smem, s>>>(n, m, lg, grid, idx, new_xyz);
+    kern<<<b, T, smem, s>>>(n, m, lg, sorted, stride, idx, new_xyz);
     return finish_launch("g4d fps_pruned kernel");
+}
+
+// sorted: per cloud n float4 (x, y, z, bits(k)) in a spatially coherent order, clouds `stride` float4 apart.  n <= 8192.
+int fps_pruned_sorted(int b, int n, int m, const float4* sorted, long long stride, int* idx, float* new_xyz, cudaStream_t s) {
+    const int bs = ref_opt_n_threads(n);
+    int lg = 0;
+    while ((1 << lg) < bs) ++lg;
+    if (n <= 1024) return launch_fps_pruned<128, 8>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
+    if (n <= 2048) return launch_fps_pruned<128, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
+    if (n <= 4096) return launch_fps_pruned<256, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
+    // Few clouds (at most one per SM, e.g. 120 per GPU when config c4 is sharded over 8 GPUs): 1024 threads x 8 points -- half
+    // the update path per step (emulation: 4.7 of 32 warps update, 150 instead of 280 instructions each); with more clouds than
+    // SMs two 512-thread CTAs per SM give the better throughput.  G4D_FPS_WIDE=0/1 overrides.
+    static const int wide_env = getenv("G4D_FPS_WIDE") ? atoi(getenv("G4D_FPS_WIDE")) : -1;
+    const bool wide = wide_env >= 0 ? wide_env != 0 : b <= sm_count();
+    if (wide) return launch_fps_pruned<1024, 8>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
+    return launch_fps_pruned<512, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
 }
 
 }  // namespace g4d
@@ -201,12 +218,5 @@ G4D_API int g4d_fps_gather_grid(int b, int n, int m, const void* grid, int* idx,
     if (b == 0 || m == 0) return 0;
     if (!grid || !idx) return bad_arg("fps_gather_grid: null pointer");
     if (n > 8192) return bad_arg("fps_gather_grid: n > 8192 (use g4d_fps_gather)");
-    const int bs = ref_opt_n_threads(n);
-    int lg = 0;
-    while ((1 << lg) < bs) ++lg;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (n <= 1024) return launch_fps_pruned<128, 8>(b, n, m, lg, (const float*)grid, idx, new_xyz, s);
-    if (n <= 2048) return launch_fps_pruned<128, 16>(b, n, m, lg, (const float*)grid, idx, new_xyz, s);
-    if (n <= 4096) return launch_fps_pruned<256, 16>(b, n, m, lg, (const float*)grid, idx, new_xyz, s);
-    return launch_fps_pruned<512, 16>(b, n, m, lg, (const float*)grid, idx, new_xyz, s);
+    return fps_pruned_sorted(b, n, m, grid_sorted((const float*)grid), (long long)(grid_cloud_words(n) / 4), idx, new_xyz, (cudaStream_t)stream);
 }

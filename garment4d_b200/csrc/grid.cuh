@@ -24,7 +24,7 @@ __host__ __device__ inline size_t grid_cloud_words(int n) {
 }
 __device__ __forceinline__ const GridHdr* grid_hdr(const float* g) { return reinterpret_cast<const GridHdr*>(g); }
 __device__ __forceinline__ const int* grid_cell_start(const float* g) { return reinterpret_cast<const int*>(g) + GRID_HDR; }
-__device__ __forceinline__ const float4* grid_sorted(const float* g) {
+__host__ __device__ __forceinline__ const float4* grid_sorted(const float* g) {
     return reinterpret_cast<const float4*>(g + (GRID_HDR + GRID_MAX_CELLS + 1 + 3) / 4 * 4);
 }
 

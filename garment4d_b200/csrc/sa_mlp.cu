@@ -172,6 +172,8 @@ struct SaMlpArgs {
     float* out_cm;                   // (b, ctot, m)
     __half* out_pm;                  // (b, m, ctot) or null
     int ctot, coff;
+    int flags;                       // bit 0: epilogue warps spin on d_full instead of the suspending wait (tuning knob G4D_SA_SPIN)
+    long long* dbg;                  // optional clock64() timeline of CTA 0 (g4d_debug_timeline); null = off
 };
 
 // Unstaged channel-major store of one output value (one centroid per tile: nsample == 128).  Out of line: code size.
@@ -358,84 +360,111 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             }
         }
     } else if (warp >= epi_warps) {
-        // =========================== MMA ISSUERS (one lane each) ============================================
+        // =========================== MMA ISSUERS ============================================================
         // Issuer i serves the slots s = i, i + ni, ...  Static schedule per round of nslot tiles:
         //   layer 1 of its slots, layer 2 of its slots, layer 3 of its slots; a layer of slot s waits for the epilogue of the
         //   previous stage of THAT slot only, which had the other slots' MMAs to finish under.
-        const int issuer = warp - epi_warps;
-        if (lane == 0) {
-            mbar_wait(bar_w, 0);
-            const uint32_t ring_lo = desc_lo(s_ring, TILE_M * 16), w1_lo = desc_lo(s_w1, L.c1 * 16), w1_step = (uint32_t)(2 * L.c1 * 16) >> 4;
-            const uint32_t w2_lo = desc_lo(s_w2, L.c2 * 16), w2_step = (uint32_t)(2 * L.c2 * 16) >> 4;
-            const uint32_t w3_step = (uint32_t)(2 * L.c3p * 16) >> 4, h_step = (uint32_t)(2 * TILE_M * 16) >> 4;
-            const uint32_t ones_lo = desc_lo(s_ones, TILE_M * 16);
-            const uint32_t idesc1 = umma_idesc(TILE_M, L.c1), idesc2 = umma_idesc(TILE_M, L.c2), idesc3 = umma_idesc(128, TILE_M);
-            uint32_t nepi[MAX_SLOTS] = {0, 0, 0, 0};              // epilogue hand-offs waited for, per slot
-            const int wave = S < RING ? S : RING;
-            for (int q0 = 0; q0 < nq; q0 += nslot) {
-                // ---- layer 1: needs the slot's TMEM drained by the previous tile's epilogue 3, and the tile's K-slices
+        // The WHOLE warp runs this code converged, on warp-uniform values only (loop counters, barrier addresses, descriptors),
+        // and one elected lane issues: tcgen05.mma / tcgen05.commit take their operands from uniform registers, and with
+        // per-thread operands inside an `if (lane == 0)` ptxas wraps EVERY one of them in an ELECT + 5 x R2UR.BROADCAST +
+        // BRA.U.ANY loop (measured: 600-900 cycles to issue a layer of 1-3 MMAs; profiles/r02_sa_timeline.txt).
+        const int issuer = __shfl_sync(0xFFFFFFFFu, warp - epi_warps, 0);
+        const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
+        mbar_wait(bar_w, 0);
+        const uint32_t ring_lo = desc_lo(s_ring, TILE_M * 16), w1_lo = desc_lo(s_w1, L.c1 * 16), w1_step = (uint32_t)(2 * L.c1 * 16) >> 4;
+        const uint32_t w2_lo = desc_lo(s_w2, L.c2 * 16), w2_step = (uint32_t)(2 * L.c2 * 16) >> 4;
+        const uint32_t w3_step = (uint32_t)(2 * L.c3p * 16) >> 4, h_step = (uint32_t)(2 * TILE_M * 16) >> 4;
+        const uint32_t ones_lo = desc_lo(s_ones, TILE_M * 16);
+        const uint32_t idesc1 = umma_idesc(TILE_M, L.c1), idesc2 = umma_idesc(TILE_M, L.c2), idesc3 = umma_idesc(128, TILE_M);
+        long long* dbg = (a.dbg && blockIdx.x == 0 && issuer == 0 && lane == 0) ? a.dbg : nullptr;    // timeline (debug): [0..5] = after-wait / after-commit stamps of layers 1,2,3 of slot 0
+        const int wave = S < RING ? S : RING;
+        const int nk1 = L.c1 / 16, nk2 = L.c2 / 16;
+        // epilogue hand-offs of a slot complete in the order (tile 0: TMEM free*, e1, e2 | tile 1: e3 of tile 0, e1, e2 | ..):
+        // the wait before layer l of round r is the (3r + l)-th of its slot, whatever the slot (* = passes at once)
+        uint32_t nepi = 0;
+        for (int q0 = 0; q0 < nq; q0 += nslot, nepi += 3) {
+            // ---- layer 1: needs the slot's TMEM drained by the previous tile's epilogue 3, and the tile's K-slices
 #pragma unroll 1
-                for (int s = issuer; s < nslot && q0 + s < nq; s += ni) {
-                    mbar_wait_spin(bar_epi + 8 * s, (nepi[s] + 1) & 1); ++nepi[s];
-                    tc_fence_after();
-                    const uint32_t it0 = (uint32_t)(q0 + s) * (uint32_t)S;
-                    uint32_t slot = it0 % RING, ph = (it0 / RING) & 1;
-                    uint32_t blo = w1_lo;
-                    const uint32_t dcol = tmem + s * L.cstride;
+            for (int s = issuer; s < nslot && q0 + s < nq; s += ni) {
+                mbar_wait_spin(bar_epi + 8 * s, (nepi + 1) & 1);
+                tc_fence_after();
+                if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 0] = clock64();
+                const uint32_t it0 = (uint32_t)(q0 + s) * (uint32_t)S;
+                uint32_t slot = it0 % RING, ph = (it0 / RING) & 1;
+                uint32_t blo = w1_lo;
+                const uint32_t dcol = tmem_u + s * L.cstride;
 #pragma unroll 1
-                    for (int w0 = 0; w0 < S; w0 += wave) {
-                        const int w1 = (w0 + wave < S) ? w0 + wave : S;
-                        // every producer warp arrives on a tile's slices in order, so the LAST slice of a wave being complete
-                        // means all of them are: one wait per wave instead of one per slice (each try_wait costs ~90 cycles)
-                        {
-                            uint32_t ls = slot + (uint32_t)(w1 - w0 - 1), lph = ph;
-                            if (ls >= (uint32_t)RING) { ls -= RING; lph ^= 1; }
-                            if constexpr (FEAT) mbar_wait(bar_full + 8 * ls, lph);   // gathers in flight: leave the issue slots to the producers
-                            else mbar_wait_spin(bar_full + 8 * ls, lph);
-                            tc_fence_after();
-                        }
+                for (int w0 = 0; w0 < S; w0 += wave) {
+                    const int w1 = (w0 + wave < S) ? w0 + wave : S;
+                    // every producer warp arrives on a tile's slices in order, so the LAST slice of a wave being complete
+                    // means all of them are: one wait per wave instead of one per slice (each try_wait costs ~90 cycles)
+                    {
+                        uint32_t ls = slot + (uint32_t)(w1 - w0 - 1), lph = ph;
+                        if (ls >= (uint32_t)RING) { ls -= RING; lph ^= 1; }
+                        if constexpr (FEAT) mbar_wait(bar_full + 8 * ls, lph);   // gathers in flight: leave the issue slots to the producers
+                        else mbar_wait_spin(bar_full + 8 * ls, lph);
+                        tc_fence_after();
+                    }
+                    if (elect_one_sync()) {
+                        uint32_t e_slot = slot, e_blo = blo;      // private walk of the elected lane: the warp's copies stay uniform
 #pragma unroll 1
                         for (int sl = w0; sl < w1; ++sl) {
-                            umma_f16(dcol, desc64(ring_lo + slot * (SLICE_BYTES >> 4)), desc64(blo), idesc1, sl > 0);
-                            umma_commit(bar_empty + 8 * slot);        // slot reusable once this (and earlier) MMAs retire
-                            blo += w1_step;
-                            if (++slot == (uint32_t)RING) { slot = 0; ph ^= 1; }
+                            umma_f16(dcol, desc64(ring_lo + e_slot * (SLICE_BYTES >> 4)), desc64(e_blo), idesc1, sl > 0);
+                            umma_commit(bar_empty + 8 * e_slot);      // slot reusable once this (and earlier) MMAs retire
+                            e_blo += w1_step;
+                            if (++e_slot == (uint32_t)RING) e_slot = 0;
                         }
+                        if (w1 == S) umma_commit(bar_dfull + 8 * s);
                     }
-                    umma_commit(bar_dfull + 8 * s);
+                    __syncwarp();
+                    slot += (uint32_t)(w1 - w0); if (slot >= (uint32_t)RING) { slot -= RING; ph ^= 1; }
+                    blo += (uint32_t)(w1 - w0) * w1_step;
                 }
-                // ---- layer 2: needs H1 written by epilogue 1; the bias enters through the constant ones operand
+                if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 1] = clock64();
+            }
+            // ---- layer 2: needs H1 written by epilogue 1; the bias enters through the constant ones operand
 #pragma unroll 1
-                for (int s = issuer; s < nslot && q0 + s < nq; s += ni) {
-                    mbar_wait_spin(bar_epi + 8 * s, (nepi[s] + 1) & 1); ++nepi[s];
-                    tc_fence_after();
+            for (int s = issuer; s < nslot && q0 + s < nq; s += ni) {
+                mbar_wait_spin(bar_epi + 8 * s, (nepi + 2) & 1);
+                tc_fence_after();
+                if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 2] = clock64();
+                if (elect_one_sync()) {
                     uint32_t alo = desc_lo(s_h + s * L.h_bytes, TILE_M * 16), blo = w2_lo;
-                    const uint32_t dcol = tmem + s * L.cstride;
-                    for (int k = 0; k < L.c1 / 16; ++k) {
+                    const uint32_t dcol = tmem_u + s * L.cstride;
+#pragma unroll 1
+                    for (int k = 0; k < nk1; ++k) {
                         umma_f16(dcol, desc64(alo), desc64(blo), idesc2, k > 0);
                         alo += h_step; blo += w2_step;
                     }
                     umma_f16(dcol, desc64(ones_lo), desc64(blo), idesc2, 1);
                     umma_commit(bar_dfull + 8 * s);
                 }
-                // ---- layer 3, transposed: D3[c3p x 128] = W3 . H2^T
+                __syncwarp();
+                if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 3] = clock64();
+            }
+            // ---- layer 3, transposed: D3[c3p x 128] = W3 . H2^T
 #pragma unroll 1
-                for (int s = issuer; s < nslot && q0 + s < nq; s += ni) {
-                    mbar_wait_spin(bar_epi + 8 * s, (nepi[s] + 1) & 1); ++nepi[s];
-                    tc_fence_after();
-                    const uint32_t dcol = tmem + s * L.cstride;
+            for (int s = issuer; s < nslot && q0 + s < nq; s += ni) {
+                mbar_wait_spin(bar_epi + 8 * s, (nepi + 3) & 1);
+                tc_fence_after();
+                if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 4] = clock64();
+                if (elect_one_sync()) {
+                    const uint32_t dcol = tmem_u + s * L.cstride;
+#pragma unroll 1
                     for (int j = 0; j < L.nb3; ++j) {
                         uint32_t alo = desc_lo(s_w3 + (uint32_t)j * 128 * 16, L.c3p * 16), blo = desc_lo(s_h + s * L.h_bytes, TILE_M * 16);
-                        for (int k = 0; k < L.c2 / 16; ++k) {
+#pragma unroll 1
+                        for (int k = 0; k < nk2; ++k) {
                             umma_f16(dcol + j * 128, desc64(alo), desc64(blo), idesc3, k > 0);
                             alo += w3_step; blo += h_step;
                         }
                     }
                     umma_commit(bar_dfull + 8 * s);
                 }
+                __syncwarp();
+                if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 5] = clock64();
             }
         }
-        __syncwarp();                                            // reconverge before the block-wide barrier below
     } else {
         // =========================== EPILOGUE: warp 4s+q owns TMEM lanes 32q .. 32q+31 of slot s ===============
         mbar_wait(bar_w, 0);                                      // b3 lives in the weight blob
@@ -446,6 +475,8 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         const uint32_t dfull = bar_dfull + 8 * slot, epi = bar_epi + 8 * slot;
         constexpr int G = TILE_M / NS;                            // centroids per tile
         uint32_t nd = 0;                                          // d_full hand-offs waited for
+        // timeline (debug): slot 0 of CTA 0, first 16 tiles: [8..13] = wake/arrive stamps of epilogues 1,2,3 (warp 0, lane 0)
+        long long* dbg = (a.dbg && blockIdx.x == 0 && warp == 0 && lane == 0) ? a.dbg : nullptr;
         // Channel-major fp32 output: with lane = channel a direct store would touch 32 different sectors per instruction
         // (4 useful bytes each).  The tile's (channel x centroid) block is staged in the slot's H buffer (free during
         // epilogue 3) and written out with lanes along the centroid index.
@@ -457,8 +488,10 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             // ---- epilogues 1 and 2: D -> ReLU -> fp16 -> H (bias already inside D; H1 is dead when d_full fires for layer 2)
 #pragma unroll 1
             for (int layer = 0; layer < 2; ++layer) {
-                mbar_wait(dfull, nd & 1); ++nd;
+                if (a.flags & 1) mbar_wait_spin(dfull, nd & 1); else mbar_wait(dfull, nd & 1);
+                ++nd;
                 tc_fence_after();
+                if (dbg && q < 16 * nslot) dbg[(q / nslot) * 16 + 8 + 2 * layer] = clock64();
                 const int ncols = layer ? L.c2 : L.c1;
                 uint4* hd = reinterpret_cast<uint4*>(hbuf);
                 int c = 0;
@@ -467,6 +500,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                     uint32_t v[32];
                     tmem_ld32_raw(taddr + c, v);
                     tmem_ld_wait<32>(v);
+                    if (dbg && layer == 0 && c == 0 && q < 16 * nslot) dbg[(q / nslot) * 16 + 6] = clock64();
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         hd[(size_t)((c >> 3) + u) * TILE_M + row] =
@@ -483,14 +517,19 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                             make_uint4(pack_relu_bits(v[8 * u], v[8 * u + 1]), pack_relu_bits(v[8 * u + 2], v[8 * u + 3]),
                                        pack_relu_bits(v[8 * u + 4], v[8 * u + 5]), pack_relu_bits(v[8 * u + 6], v[8 * u + 7]));
                 }
+                if (dbg && layer == 0 && q < 16 * nslot) dbg[(q / nslot) * 16 + 7] = clock64();
                 tc_fence_before();
                 fence_proxy_async();
+                if (dbg && layer == 0 && q < 16 * nslot) dbg[(q / nslot) * 16 + 14] = clock64();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(epi);
+                if (dbg && q < 16 * nslot) dbg[(q / nslot) * 16 + 9 + 2 * layer] = clock64();
             }
             // ---- epilogue 3: lane = output channel; max over each neighbourhood's nsample consecutive columns
-            mbar_wait(dfull, nd & 1); ++nd;
+            if (a.flags & 1) mbar_wait_spin(dfull, nd & 1); else mbar_wait(dfull, nd & 1);
+            ++nd;
             tc_fence_after();
+            if (dbg && q < 16 * nslot) dbg[(q / nslot) * 16 + 12] = clock64();
             const unsigned gp0 = (unsigned)tile * (unsigned)G;    // first centroid of the tile
             const unsigned cloud0 = gp0 / (unsigned)a.m, p0 = gp0 - cloud0 * (unsigned)a.m;
 #pragma unroll 1
@@ -529,9 +568,11 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                     }
                 }
             }
+            if (dbg && q < 16 * nslot) dbg[(q / nslot) * 16 + 15] = clock64();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(epi);                      // TMEM drained: the slot's next tile may start layer 1
+            if (dbg && q < 16 * nslot) dbg[(q / nslot) * 16 + 13] = clock64();
             if (staged) {
                 slot_bar_sync(slot);                              // the 4 warps of this slot only
                 const int et = quad * 32 + lane;                  // 0..127
@@ -556,6 +597,12 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
 }  // namespace g4d
 
 using namespace g4d;
+
+static long long* g_timeline = nullptr;
+// Debug aid: device buffer of >= 16*16 int64 that CTA 0 of the next g4d_sa_mlp_max launches fills with clock64() stamps of
+// its slot 0 (per tile: issuer [0..5] = after-wait / after-commit of layers 1-3, epilogue warp 0 [8..13] = wake / arrive of
+// epilogues 1-3); NULL switches it off.
+G4D_API void g4d_debug_timeline(void* buf) { g_timeline = (long long*)buf; }
 
 G4D_API int g4d_sa_mlp_k0(int c_in) { return (c_in + XYZ_SLOTS + 15) / 16 * 16; }
 
@@ -643,6 +690,9 @@ G4D_API int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int
     a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.feat_pm = (const __half*)feat_pm;
     a.params = (const unsigned char*)params_dev;
     a.out_cm = out_cm; a.out_pm = (__half*)out_pm; a.ctot = out_c_total; a.coff = out_c_off;
+    static const int spin = env_int("G4D_SA_SPIN", 0);
+    a.flags = spin ? 1 : 0;
+    a.dbg = g_timeline;
 
     typedef void (*kern_t)(const SaMlpArgs);
     kern_t kern = nullptr;

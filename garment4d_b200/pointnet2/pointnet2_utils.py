@@ -16,6 +16,7 @@ module).  Two fused entry points are added behind the same operators:
 ``furthest_point_sample_and_gather`` (FPS + centroid gather, one launch) and the single-kernel
 ``QueryAndGroup.forward``.
 """
+import os
 from typing import Tuple
 
 import torch
@@ -76,6 +77,9 @@ def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 
 GRID_MIN_POINTS = 2048     # below this the brute-force scans are already cheap
 FPS_PRUNE_MIN_POINTS = 2048
+# "rows": Morton-ordered warp-row pruned kernel (fps_rows.cu, default); "pruned": the cell-sorted thread-per-clump kernel of
+# round 1 (fps_pruned.cu, needs a grid, n <= 8192); "plain": no pruning (fps.cu)
+FPS_KERNEL = os.environ.get("G4D_FPS", "rows")
 
 
 def build_grid(xyz: torch.Tensor, min_cell: float) -> torch.Tensor:
@@ -131,7 +135,13 @@ def furthest_point_sample_and_gather(xyz: torch.Tensor, npoint: int) -> Tuple[to
     B, N, _ = xyz.size()
     idx = _i32(B, npoint, device=xyz.device)
     new_xyz = _f32(B, npoint, 3, device=xyz.device)
-    if FPS_PRUNE_MIN_POINTS <= N <= 8192:
+    if FPS_KERNEL == "rows" and FPS_PRUNE_MIN_POINTS <= N <= 16384:
+        L = _lib.lib()
+        ws = torch.empty(L.g4d_fps_workspace_bytes(B, N) // 4, dtype=torch.float32, device=xyz.device)
+        rc = L.g4d_fps_gather_ws(B, N, npoint, _lib.ptr(xyz), _lib.ptr(idx), _lib.ptr(new_xyz), _lib.ptr(ws), _lib.stream_ptr())
+        _lib.check(rc, "g4d_fps_gather_ws")
+        return idx, new_xyz
+    if FPS_KERNEL == "pruned" and FPS_PRUNE_MIN_POINTS <= N <= 8192:
         # exact spatial pruning over the cell-sorted order (any grid over xyz will do; an SA module builds it with its
         # largest ball-query radius first, so the ball query that follows re-uses it)
         grid = _cached_grid(xyz)

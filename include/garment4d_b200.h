@@ -104,6 +104,12 @@ int g4d_grid_build(int b, int n, const float* xyz, float min_cell, void* grid, v
 /* = g4d_fps_gather (identical idx / new_xyz) given any grid over xyz: threads own compact clumps of the cell-sorted
  * points and skip, exactly, every min-distance update that cannot change anything.  1 <= n <= 8192. */
 int g4d_fps_gather_grid(int b, int n, int m, const void* grid, int* idx, float* new_xyz, void* stream);
+/* = g4d_fps_gather (identical idx / new_xyz) through the Morton-ordered, warp-row pruned kernel (fps_rows.cu): the cloud is
+ * first sorted by the 15-bit Morton code of a 32^3 grid over its bounding cube, 32 consecutive points form a clump that all
+ * 32 lanes of a warp update together.  1 <= n <= 16384.  workspace: device buffer of g4d_fps_workspace_bytes(b, n),
+ * 16-byte aligned (the sorted copy; scratch). */
+size_t g4d_fps_workspace_bytes(int b, int n);
+int g4d_fps_gather_ws(int b, int n, int m, const float* xyz, int* idx, float* new_xyz, void* workspace, void* stream);
 /* = g4d_ball_query2 (idx1 = NULL: = g4d_ball_query) given a grid over xyz with min_cell >= max radius; n <= 65536 */
 int g4d_ball_query2_grid(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
                          const float* new_xyz, const void* grid, void* stream);
@@ -139,6 +145,10 @@ int g4d_sa_mlp_pack_params(const g4d_sa_mlp_desc* d, const float* w1, const floa
 int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int b, int n, int m, const float* xyz,
                    const float* new_xyz, const int* idx, const void* feat_pm, float* out_cm, void* out_pm,
                    int out_c_total, int out_c_off, void* stream);
+
+/* debug aid: clock64() timeline of slot 0 of CTA 0 of the following g4d_sa_mlp_max launches (buf: >= 256 int64 on the device;
+ * NULL = off) */
+void g4d_debug_timeline(void* buf);
 
 /* Fused feature propagation (no skip features) + optional segmentation head on tcgen05: inverse-distance weights
  * from three_nn's squared distances, 3-tap interpolation, the FP module's 2-layer 1x1-conv MLP (eval BN folded, ReLU)

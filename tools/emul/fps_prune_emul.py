@@ -112,3 +112,24 @@ if __name__ == "__main__" and len(sys.argv) > 2:
         for dname, d in designs.items():
             c, i = cost_model(p, order, m, d)
             print(f"{kind:5s} {oname:18s} {dname:32s} busiest sub-partition {c:7.1f}   total {i:7.1f}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 3:
+    print("warp-row design: flagged 32-point clumps per step / warps with any flagged clump")
+    for oname, order in [("coarse row-major", order_coarse_rowmajor(p, 0.1)), ("morton 4b", order_morton(p, 4)), ("morton 5b", order_morton(p, 5))]:
+        q = p[order].astype(np.float64)
+        cl = q.reshape(-1, 32, 3); nc = cl.shape[0]
+        ctr = 0.5 * (cl.min(1) + cl.max(1)); rad = np.sqrt(((cl - ctr[:, None]) ** 2).sum(2).max(1)) * 1.0001
+        temp = np.full(cl.shape[:2], 1e10); thr = np.full(nc, np.inf)
+        last = q[np.where(order == 0)[0][0]]
+        nf, nw, mx = [], [], []
+        for j in range(1, m):
+            need = ((ctr - last) ** 2).sum(1) < thr
+            if j == 1: need[:] = True
+            idxs = np.where(need)[0]
+            temp[idxs] = np.minimum(temp[idxs], ((cl[idxs] - last) ** 2).sum(2))
+            thr[idxs] = (rad[idxs] + np.sqrt(temp[idxs].max(1))) ** 2 * 1.0002
+            last = cl.reshape(-1, 3)[temp.argmax()]
+            pw = need.reshape(-1, 16).sum(1)
+            if j > 1: nf.append(need.sum()); nw.append((pw > 0).sum()); mx.append(pw.max())
+        print(f"{kind:5s} {oname:18s} flagged clumps/step {np.mean(nf):5.2f}  warps touched {np.mean(nw):4.2f}  max flagged in one warp: mean {np.mean(mx):4.2f} p95 {np.percentile(mx,95):.0f}")
