@@ -70,6 +70,7 @@ _SIGNATURES = {
     "g4d_bias_relu_unpack": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "g4d_bias_relu_pm": (_i, [_i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "g4d_batch_rodrigues": (_i, [_i, _vp, _vp, _vp]),
+    "g4d_blend_shapes": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "g4d_vertices2joints": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "g4d_batch_rigid_transform": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_lbs_skin": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -72,11 +72,15 @@ static bool fp_layout(const g4d_fp_desc* d, FpLayout* L, const char** why) {
     // keep ~24 KB of the SM's shared memory free: Nsight Compute cannot replay a kernel that takes all 227 KB (the first
     // version of this layout did, and every capture of it hung), and the L1 that is left serves the gather
     const uint32_t budget = 203u * 1024u;
-    if (L->off_a + (FP_CG + 1) * L->a_bytes > 227u * 1024u) { *why = "fp: shared memory footprint exceeds 227 KB"; return false; }
+    if (L->off_a + 2 * L->a_bytes > 227u * 1024u) { *why = "fp: shared memory footprint exceeds 227 KB"; return false; }
     uint32_t na = budget > L->off_a ? (budget - L->off_a) / L->a_bytes : 0;
-    if (na < (uint32_t)FP_CG + 1) na = FP_CG + 1;          // each consumer group holds one buffer: at least one more to fill
-    L->na = na > (uint32_t)FP_MAX_A ? (uint32_t)FP_MAX_A : na;
-    if (const char* e = getenv("G4D_FP_NA")) { const int v = atoi(e); if (v >= FP_CG + 1 && (uint32_t)v <= L->na) L->na = (uint32_t)v; }   // tuning knob
+    // The ring depth must be EVEN: tile i lives in buffer i % na and is filled by producer group i % 2 and drained by consumer
+    // group i % 2, so with an even depth every buffer has ONE filler and ONE drainer, each seeing its phases in order -- the
+    // single phase bit of an mbarrier is only safe then (with 3 buffers a producer group could run a lap ahead of a lagging
+    // consumer group and pass its "empty" wait on the wrong phase).  4 when they fit (one tile of run-ahead per group), else 2.
+    (void)budget;
+    na = (L->off_a + 4 * L->a_bytes <= 227u * 1024u) ? 4 : 2;     // (the encoder's shapes need 200 KB with 4: inside the profiling budget)
+    L->na = na;
     L->total_smem = L->off_a + L->na * L->a_bytes;
     uint32_t p2 = 32;
     while (p2 < (uint32_t)hmax || p2 < (uint32_t)L->h2p) p2 <<= 1;

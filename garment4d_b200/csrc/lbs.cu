@@ -64,7 +64,7 @@ __global__ void lbs_shape_kernel(int F, int V3, int NB, int betas_rows, const fl
                                  float* __restrict__ v_shaped) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= V3) return;
-    const float vt = __ldg(v_template + e);
+    const float vt = v_template ? __ldg(v_template + e) : 0.f;      // null template: the displacement alone (blend_shapes)
     const float* sd = shapedirs + (size_t)e * NB;
     for (int f = blockIdx.y; f < F; f += gridDim.y) {
         const float* bt = betas + (size_t)(betas_rows == 1 ? 0 : f) * NB;
@@ -304,6 +304,18 @@ G4D_API int g4d_batch_rodrigues(int n, const float* rot_vecs, float* rot_mats, v
     if (n == 0) return 0;
     batch_rodrigues_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, rot_vecs, rot_mats);
     return finish_launch("g4d batch_rodrigues");
+}
+
+// blend_shapes (lbs.py:288-309): out[f, v, k] = sum_l betas[f, l] * shape_disps[v, k, l];  betas (F, NB), shape_disps (V, 3, NB),
+// out (F, V, 3).
+G4D_API int g4d_blend_shapes(int F, int V, int NB, const float* betas, const float* shape_disps, float* out, void* stream) {
+    if (F < 0 || V < 0 || NB < 0) return bad_arg("blend_shapes: negative size");
+    if (F == 0 || V == 0) return 0;
+    if (!betas || !shape_disps || !out) return bad_arg("blend_shapes: null pointer");
+    const int V3 = V * 3;
+    dim3 grid((V3 + 255) / 256, F < 64 ? F : 64);
+    lbs_shape_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, V3, NB, F, betas, nullptr, shape_disps, out);
+    return finish_launch("g4d blend_shapes");
 }
 
 // vertices2joints / vertices2jointsB (lbs.py:251-286).  per_frame_regressor = 0: J_regressor (J,V); 1: (F,J,V).

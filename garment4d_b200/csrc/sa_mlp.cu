@@ -51,12 +51,16 @@ constexpr int MAX_SLOTS = 4;
 constexpr int PROD_WARPS = 8;                 // two groups of 4
 // barrier block: [0] weights, [1] tmem address slot, [2 .. 2+MAX_SLOTS) d_full[s], [.. +MAX_SLOTS) epi_done[s],
 //                then full[MAX_RING], empty[MAX_RING]
-constexpr int BAR_WORDS = 2 + 2 * MAX_SLOTS + 2 * MAX_RING;
+//                then h1_full[MAX_SLOTS][2], h_free[MAX_SLOTS][2] (xyz-only levels: layer 1 runs in the producers)
+constexpr int BAR_WORDS = 2 + 2 * MAX_SLOTS + 2 * MAX_RING + 4 * MAX_SLOTS;
 
 struct SaMlpLayout {
     int k0, c1, c2, c3, c3p, nb3, nslices, ring, nslot, ni, threads;
     uint32_t h_bytes, cstride;                              // per-slot H buffer bytes, per-slot TMEM column stride
-    uint32_t off_w1, off_w2, off_w3, off_b3, off_ones, blob_bytes;   // inside the parameter blob == smem image
+    uint32_t off_w1, off_w2, off_w3, off_b3, off_ones, off_w1f, blob_bytes;   // inside the parameter blob == smem image
+    uint32_t off_stage, stage_bytes;                        // per-slot staging area of the channel-major output
+    int feat, nhbuf;                                        // features present; H buffers per slot (2 when layer 1 runs in the producers)
+    int c3r, rep;                                           // layer 3 with c3 <= 64: W3 replicated rep = 128/c3r times down the 128 TMEM lanes
     uint32_t off_h, off_ring, off_bar, total_smem;
     uint32_t tmem_cols;
 };
@@ -88,6 +92,18 @@ static bool make_layout(const g4d_sa_mlp_desc* d, SaMlpLayout* L, const char** w
     L->off_w3 = o; o += (uint32_t)L->c2 * L->c3p * 2;
     L->off_b3 = o; o += (uint32_t)L->c3p * 4;
     L->off_ones = o; o += SLICE_BYTES;                            // constant A operand of the bias MMA
+    L->off_w1f = o; o += d->c_in > 0 ? 0u : (uint32_t)L->c1 * 16;  // fp32 (wx, wy, wz, b) per channel: layer 1 of xyz-only levels on CUDA cores
+    L->feat = d->c_in > 0;
+    L->nhbuf = L->feat ? 1 : 2;
+    // Layer 3 is transposed (channels on TMEM lanes).  With c3 <= 64 half or three quarters of the 128 lanes would hold zero
+    // padding and their epilogue warps would idle while the others walk all 128 position columns: instead W3 is REPLICATED
+    // down the lanes (same MMA, no extra cost) and copy cp serves the position columns [cp * 128/rep, (cp+1) * 128/rep) --
+    // every warp reads 128/rep columns.  A neighbourhood (nsample columns) must not straddle two copies.
+    L->c3r = 128; L->rep = 1;
+    if (L->c3p == 128) {
+        const int r = d->c3 <= 32 ? 32 : (d->c3 <= 64 ? 64 : 128);
+        if (128 / r > 1 && d->nsample <= 128 / (128 / r)) { L->c3r = r; L->rep = 128 / r; }
+    }
     L->blob_bytes = o;                                            // multiple of 16 by construction
     const int hk = L->c1 > L->c2 ? L->c1 : L->c2;
     L->h_bytes = (uint32_t)TILE_M * hk * 2;
@@ -101,11 +117,16 @@ static bool make_layout(const g4d_sa_mlp_desc* d, SaMlpLayout* L, const char** w
     // as many slots as shared memory allows while the ring still holds two tiles' worth of slices (the producers must
     // run a tile ahead of the issuer); a single slot only needs a ring of two slices
     bool ok = false;
-    for (; nslot >= 1; --nslot) {
-        const uint32_t fixed = L->off_h + (uint32_t)nslot * L->h_bytes + bar_bytes;
-        if (fixed + 2u * SLICE_BYTES > budget) continue;
+    // channel-major output staging: inside the H buffer when features are present (H is free during epilogue 3); a separate
+    // area for xyz-only levels, whose H buffers are refilled by the producers meanwhile
+    const int G = TILE_M / d->nsample;
+    L->stage_bytes = L->feat ? 0u : round_up((uint32_t)L->c3 * (uint32_t)(G + 1) * 4u, 128u);
+    for (; nslot >= 1; nslot >>= 1) {                             // 4, 2, 1: two issuers take the tiles of even / odd q
+        const uint32_t fixed = L->off_h + (uint32_t)nslot * ((uint32_t)L->nhbuf * L->h_bytes + L->stage_bytes) + bar_bytes;
+        if (fixed + 4u * SLICE_BYTES > budget) continue;
         int ring = (int)((budget - fixed) / SLICE_BYTES);
         if (ring > MAX_RING) ring = MAX_RING;
+        if (nslot >= 2) ring &= ~1;                               // two issuers: two sub-rings of ring / 2 slices
         const int want = 2 * L->nslices < MAX_RING ? 2 * L->nslices : MAX_RING;
         if (nslot > 1 && ring < want) continue;
         L->nslot = nslot; L->ring = ring; ok = true;
@@ -115,7 +136,8 @@ static bool make_layout(const g4d_sa_mlp_desc* d, SaMlpLayout* L, const char** w
     L->ni = L->nslot >= 2 ? 2 : 1;
     { const int v = env_int("G4D_SA_NI", 0); if (v >= 1 && v <= 2 && v <= L->nslot) L->ni = v; }
     L->threads = (4 * L->nslot + L->ni + PROD_WARPS) * 32;
-    L->off_ring = L->off_h + (uint32_t)L->nslot * L->h_bytes;
+    L->off_stage = L->off_h + (uint32_t)L->nslot * (uint32_t)L->nhbuf * L->h_bytes;
+    L->off_ring = L->off_stage + (uint32_t)L->nslot * L->stage_bytes;
     L->off_bar = L->off_ring + (uint32_t)L->ring * SLICE_BYTES;
     L->total_smem = L->off_bar + bar_bytes;
     uint32_t p2 = 32;
@@ -207,6 +229,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
     const uint32_t bar_w = bar0, tmem_slot = bar0 + 8;
     const uint32_t bar_dfull = bar0 + 16, bar_epi = bar_dfull + 8 * MAX_SLOTS;
     const uint32_t bar_full = bar_epi + 8 * MAX_SLOTS, bar_empty = bar_full + 8 * MAX_RING;
+    const uint32_t bar_h1full = bar_empty + 8 * MAX_RING, bar_hfree = bar_h1full + 16 * MAX_SLOTS;      // [slot][buf]
     const uint32_t s_w1 = smem_u32(smem + L.off_w1), s_w2 = smem_u32(smem + L.off_w2), s_w3 = smem_u32(smem + L.off_w3);
     const uint32_t s_ones = smem_u32(smem + L.off_ones);
     const uint32_t s_h = smem_u32(smem + L.off_h), s_ring = smem_u32(smem + L.off_ring);
@@ -214,6 +237,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
     if (tid == 0) {
         mbar_init(bar_w, 1);
         for (int s = 0; s < nslot; ++s) { mbar_init(bar_dfull + 8 * s, 1); mbar_init(bar_epi + 8 * s, 4); }
+        for (int s = 0; s < 2 * nslot; ++s) { mbar_init(bar_h1full + 8 * s, 4); mbar_init(bar_hfree + 8 * s, 1); }
         for (int r = 0; r < L.ring; ++r) { mbar_init(bar_full + 8 * r, 4);     /* the 4 warps of the producer group that owns the slot's tile */ mbar_init(bar_empty + 8 * r, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -227,10 +251,17 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         bulk_g2s(smem_u32(smem), a.params, L.blob_bytes, bar_w);      // folded weights, biases, the constant ones slice: once per CTA
     }
 
-    const int S = L.nslices, RING = L.ring;
+    // With two issuers the ring is split into TWO SUB-RINGS, one per producer group (tiles of even / odd q).  A ring slot's barriers carry one
+    // phase bit, which is only safe while each side of a slot sees its phases in order: ONE group fills a sub-ring in program
+    // order and ONE issuer drains it in tile order (issuer q % 2 with two issuers -- nslot is even then --, the single issuer
+    // alternating between the sub-rings otherwise).  With a shared ring a group could run a lap ahead of the other one's
+    // unfilled slices, or an issuer see another issuer's lap: a wait then passes on the wrong phase (it hung with 3 slots).
+    // A single issuer (one slot) is fed by ONE producer group over the whole ring.
+    const int nring = L.ni == 2 ? 2 : 1;
+    const int S = L.nslices, RING = L.ring / nring;           // slices per sub-ring
     const int bx = (int)blockIdx.x, gx = (int)gridDim.x;
     // this CTA's tile sequence: tile(q) = bx + q * gx, q = 0 .. nq-1; slot of tile q = q % nslot; its slices are the
-    // global slice numbers q*S .. q*S+S-1 (ring position = number % RING)
+    // slice numbers k*S .. k*S+S-1 in the sub-ring of its issuer, k = index of the tile among that issuer's tiles
     const int nq = bx < a.ntiles ? (a.ntiles - bx + gx - 1) / gx : 0;
 
     if (warp >= epi_warps + ni) {
@@ -238,13 +269,14 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         // Two groups of 4 warps take alternate tiles of the sequence and fill the ring concurrently, in order.  Inside a
         // group the loads are software-pipelined: idx two tiles ahead, coordinates one tile ahead, the feature row of the
         // current tile entirely in flight (cp.async) before the first slice is handed over.
-        constexpr int NG = PROD_WARPS / 4;
+        const int NG = FEAT ? nring : PROD_WARPS / 4;          // groups at work (xyz-only levels have no ring: both groups always)
         const int pw = warp - (epi_warps + ni);
-        const int grp = pw >> 2;                                 // 0 .. NG-1
+        const int grp = pw >> 2;                                 // 0 .. PROD_WARPS/4-1
         const int r = (pw & 3) * 32 + lane;                      // tile row 0..127
         const int nchunk_feat = FEAT ? (a.c_in >> 3) : 0;
         const unsigned um = (unsigned)a.m;
-        int q = grp;
+        if (!FEAT) mbar_wait(bar_w, 0);                          // layer-1 weights live in the blob
+        int q = grp < NG ? grp : nq;                           // a group without work falls straight through
         int t_cur = q < nq ? bx + q * gx : a.ntiles, t_nxt = q + NG < nq ? bx + (q + NG) * gx : a.ntiles;
         int src_n = 0, src_nn = 0;
         float npx = 0.f, npy = 0.f, npz = 0.f, nqx = 0.f, nqy = 0.f, nqz = 0.f;
@@ -264,7 +296,9 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             const bool live = tile * TILE_M + r < a.total_rows;
             const float dx = npx - nqx, dy = npy - nqy, dz = npz - nqz;
             const unsigned pt = npt;
-            const uint32_t it0 = (uint32_t)q * (uint32_t)S;        // global slice number of this tile's first slice
+            // sub-ring of this group (q % 2 == grp), and the tile's slice number in it
+            const uint32_t rbase = (uint32_t)(grp * RING);
+            const uint32_t it0 = (uint32_t)(nring == 2 ? q >> 1 : q) * (uint32_t)S;
             // ---- advance the pipeline: issue the loads of the following tiles before touching this one
             q += NG;
             t_cur = t_nxt;
@@ -293,15 +327,32 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 xc1 = make_uint4(uhz | (0x3C00u << 16), 0x3C00u, 0, 0);
             }
             if (!FEAT) {
-                // xyz-only level: a single slice per tile
-                const uint32_t slot = it0 % RING, ph = (it0 / RING) & 1;
-                mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);
-                uint4* dst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
-                dst[r] = xc0;
-                dst[TILE_M + r] = xc1;
+                // xyz-only level: LAYER 1 RUNS HERE, on the CUDA cores (K = 3: 0.1 % of the FLOPs; on the tensor pipe it cost a
+                // whole MMA -> TMEM -> epilogue hand-off, ~1500 cycles of the tile's serial chain).  Each thread computes its row of
+                // H1 = relu(W1 . (dx, dy, dz) + b1) in fp32 and writes it, fp16, straight into the slot's H buffer (double-buffered:
+                // the tile after next of this slot is prepared while the current one is in layers 2-3).
+                const int q_this = q - NG;                         // q was advanced above
+                const int sl = q_this % nslot, t = q_this / nslot; // slot and index of the tile within its slot
+                const int buf = t & 1;
+                const uint32_t hf = bar_hfree + 8 * (2 * sl + buf), h1f = bar_h1full + 8 * (2 * sl + buf);
+                mbar_wait_relaxed(hf, ((t >> 1) + 1) & 1);         // layer 3 of tile t-2 has read this buffer (passes at once for t < 2)
+                uint4* hd = reinterpret_cast<uint4*>(smem + L.off_h + (size_t)(2 * sl + buf) * L.h_bytes);
+                const float4* w1f = reinterpret_cast<const float4*>(smem + L.off_w1f);
+#pragma unroll 1
+                for (int j = 0; j < (L.c1 >> 3); ++j) {
+                    uint32_t h[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 wa = w1f[8 * j + 2 * i], wb = w1f[8 * j + 2 * i + 1];          // broadcast reads
+                        const float va = fmaf(wa.z, dz, fmaf(wa.y, dy, fmaf(wa.x, dx, wa.w)));
+                        const float vb = fmaf(wb.z, dz, fmaf(wb.y, dy, fmaf(wb.x, dx, wb.w)));
+                        h[i] = pack_relu_f16x2(va, vb);
+                    }
+                    hd[(size_t)j * TILE_M + r] = live ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(0, 0, 0, 0);
+                }
                 fence_proxy_async();                              // generic-proxy stores -> visible to tcgen05.mma
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full + 8 * slot);
+                if (lane == 0) mbar_arrive(h1f);
             } else {
                 // Feature levels: every 16-byte chunk of the neighbour's fp16 row goes global -> shared with cp.async (LDGSTS), one
                 // commit group per K-slice, a whole wave of slices in flight at once (no register staging: 128 threads x 2S copies
@@ -316,9 +367,9 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 const uint32_t slot_w = slot;
 #pragma unroll 1
                 for (int sl = w0; sl < w1; ++sl) {
-                    mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);           // slot free (first lap passes at once)
-                    const uint32_t sdst = s_ring + slot * SLICE_BYTES + (uint32_t)r * 16;
-                    uint4* gdst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)slot * SLICE_BYTES);
+                    mbar_wait_relaxed(bar_empty + 8 * (rbase + slot), ph ^ 1);           // slot free (first lap passes at once)
+                    const uint32_t sdst = s_ring + (rbase + slot) * SLICE_BYTES + (uint32_t)r * 16;
+                    uint4* gdst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)(rbase + slot) * SLICE_BYTES);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int c = 2 * sl + h;                               // 16-byte chunk index along K
@@ -353,7 +404,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                     }
                     fence_proxy_async();                                        // copies + stores -> visible to tcgen05.mma
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full + 8 * slot_a);
+                    if (lane == 0) mbar_arrive(bar_full + 8 * (rbase + slot_a));
                     if (++slot_a == (uint32_t)RING) slot_a = 0;
                 }
                 }
@@ -381,15 +432,17 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         const int nk1 = L.c1 / 16, nk2 = L.c2 / 16;
         // epilogue hand-offs of a slot complete in the order (tile 0: TMEM free*, e1, e2 | tile 1: e3 of tile 0, e1, e2 | ..):
         // the wait before layer l of round r is the (3r + l)-th of its slot, whatever the slot (* = passes at once)
+        // (xyz-only levels have no layer 1 here: two hand-offs per tile)
         uint32_t nepi = 0;
-        for (int q0 = 0; q0 < nq; q0 += nslot, nepi += 3) {
+        for (int q0 = 0, rnd = 0; q0 < nq; q0 += nslot, nepi += (FEAT ? 3 : 2), ++rnd) {
             // ---- layer 1: needs the slot's TMEM drained by the previous tile's epilogue 3, and the tile's K-slices
 #pragma unroll 1
-            for (int s = issuer; s < nslot && q0 + s < nq; s += ni) {
+            for (int s = issuer; FEAT && s < nslot && q0 + s < nq; s += ni) {
                 mbar_wait_spin(bar_epi + 8 * s, (nepi + 1) & 1);
                 tc_fence_after();
                 if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 0] = clock64();
-                const uint32_t it0 = (uint32_t)(q0 + s) * (uint32_t)S;
+                const uint32_t rbase = nring == 2 ? (uint32_t)(((q0 + s) & 1) * RING) : 0u;
+                const uint32_t it0 = (uint32_t)(nring == 2 ? (q0 + s) >> 1 : q0 + s) * (uint32_t)S;      // the tile's slice number in its sub-ring
                 uint32_t slot = it0 % RING, ph = (it0 / RING) & 1;
                 uint32_t blo = w1_lo;
                 const uint32_t dcol = tmem_u + s * L.cstride;
@@ -401,16 +454,15 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                     {
                         uint32_t ls = slot + (uint32_t)(w1 - w0 - 1), lph = ph;
                         if (ls >= (uint32_t)RING) { ls -= RING; lph ^= 1; }
-                        if constexpr (FEAT) mbar_wait(bar_full + 8 * ls, lph);   // gathers in flight: leave the issue slots to the producers
-                        else mbar_wait_spin(bar_full + 8 * ls, lph);
+                        mbar_wait(bar_full + 8 * (rbase + ls), lph);   // gathers in flight: leave the issue slots to the producers
                         tc_fence_after();
                     }
                     if (elect_one_sync()) {
                         uint32_t e_slot = slot, e_blo = blo;      // private walk of the elected lane: the warp's copies stay uniform
 #pragma unroll 1
                         for (int sl = w0; sl < w1; ++sl) {
-                            umma_f16(dcol, desc64(ring_lo + e_slot * (SLICE_BYTES >> 4)), desc64(e_blo), idesc1, sl > 0);
-                            umma_commit(bar_empty + 8 * e_slot);      // slot reusable once this (and earlier) MMAs retire
+                            umma_f16(dcol, desc64(ring_lo + (rbase + e_slot) * (SLICE_BYTES >> 4)), desc64(e_blo), idesc1, sl > 0);
+                            umma_commit(bar_empty + 8 * (rbase + e_slot));      // slot reusable once this (and earlier) MMAs retire
                             e_blo += w1_step;
                             if (++e_slot == (uint32_t)RING) e_slot = 0;
                         }
@@ -425,11 +477,13 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             // ---- layer 2: needs H1 written by epilogue 1; the bias enters through the constant ones operand
 #pragma unroll 1
             for (int s = issuer; s < nslot && q0 + s < nq; s += ni) {
-                mbar_wait_spin(bar_epi + 8 * s, (nepi + 2) & 1);
+                mbar_wait_spin(bar_epi + 8 * s, (nepi + (FEAT ? 2 : 1)) & 1);     // xyz-only: the slot's TMEM drained by the previous tile
+                const int hb = FEAT ? s : 2 * s + (rnd & 1);                     // H buffer of this tile
+                if (!FEAT) mbar_wait_spin(bar_h1full + 8 * hb, (rnd >> 1) & 1);  // H1 written by the producers
                 tc_fence_after();
                 if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 2] = clock64();
                 if (elect_one_sync()) {
-                    uint32_t alo = desc_lo(s_h + s * L.h_bytes, TILE_M * 16), blo = w2_lo;
+                    uint32_t alo = desc_lo(s_h + hb * L.h_bytes, TILE_M * 16), blo = w2_lo;
                     const uint32_t dcol = tmem_u + s * L.cstride;
 #pragma unroll 1
                     for (int k = 0; k < nk1; ++k) {
@@ -445,14 +499,15 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             // ---- layer 3, transposed: D3[c3p x 128] = W3 . H2^T
 #pragma unroll 1
             for (int s = issuer; s < nslot && q0 + s < nq; s += ni) {
-                mbar_wait_spin(bar_epi + 8 * s, (nepi + 3) & 1);
+                mbar_wait_spin(bar_epi + 8 * s, (nepi + (FEAT ? 3 : 2)) & 1);
                 tc_fence_after();
                 if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 4] = clock64();
+                const int hb = FEAT ? s : 2 * s + (rnd & 1);
                 if (elect_one_sync()) {
                     const uint32_t dcol = tmem_u + s * L.cstride;
 #pragma unroll 1
                     for (int j = 0; j < L.nb3; ++j) {
-                        uint32_t alo = desc_lo(s_w3 + (uint32_t)j * 128 * 16, L.c3p * 16), blo = desc_lo(s_h + s * L.h_bytes, TILE_M * 16);
+                        uint32_t alo = desc_lo(s_w3 + (uint32_t)j * 128 * 16, L.c3p * 16), blo = desc_lo(s_h + hb * L.h_bytes, TILE_M * 16);
 #pragma unroll 1
                         for (int k = 0; k < nk2; ++k) {
                             umma_f16(dcol + j * 128, desc64(alo), desc64(blo), idesc3, k > 0);
@@ -460,6 +515,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                         }
                     }
                     umma_commit(bar_dfull + 8 * s);
+                    if (!FEAT) umma_commit(bar_hfree + 8 * hb);   // the producers may refill this H buffer once layer 3 has read it
                 }
                 __syncwarp();
                 if (dbg && s == 0 && q0 < 16 * nslot) dbg[(q0 / nslot) * 16 + 5] = clock64();
@@ -471,7 +527,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         const int slot = warp >> 2, quad = warp & 3;
         const int row = quad * 32 + lane;                         // tile row (layers 1-2) / channel within block (layer 3)
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + slot * L.cstride;
-        unsigned char* hbuf = smem + L.off_h + (size_t)slot * L.h_bytes;
+        unsigned char* const hbuf0 = smem + L.off_h + (size_t)slot * L.nhbuf * L.h_bytes;
         const uint32_t dfull = bar_dfull + 8 * slot, epi = bar_epi + 8 * slot;
         constexpr int G = TILE_M / NS;                            // centroids per tile
         uint32_t nd = 0;                                          // d_full hand-offs waited for
@@ -480,14 +536,15 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
         // Channel-major fp32 output: with lane = channel a direct store would touch 32 different sectors per instruction
         // (4 useful bytes each).  The tile's (channel x centroid) block is staged in the slot's H buffer (free during
         // epilogue 3) and written out with lanes along the centroid index.
-        const bool staged = G >= 2 && (size_t)L.c3 * (G + 1) * 4 <= (size_t)L.h_bytes;
-        float* stage = reinterpret_cast<float*>(hbuf);
+        const bool staged = G >= 2 && (size_t)L.c3 * (G + 1) * 4 <= (size_t)(FEAT ? L.h_bytes : L.stage_bytes);
+        float* stage = reinterpret_cast<float*>(FEAT ? hbuf0 : smem + L.off_stage + (size_t)slot * L.stage_bytes);
 #pragma unroll 1
         for (int q = slot; q < nq; q += nslot) {
             const int tile = bx + q * gx;
-            // ---- epilogues 1 and 2: D -> ReLU -> fp16 -> H (bias already inside D; H1 is dead when d_full fires for layer 2)
+            unsigned char* hbuf = FEAT ? hbuf0 : hbuf0 + (size_t)((q / nslot) & 1) * L.h_bytes;      // xyz-only: double-buffered
+            // ---- epilogues 1 and 2 (xyz-only levels: only 2 -- layer 1 ran in the producers): D -> ReLU -> fp16 -> H (bias already inside D; H1 is dead when d_full fires for layer 2)
 #pragma unroll 1
-            for (int layer = 0; layer < 2; ++layer) {
+            for (int layer = FEAT ? 0 : 1; layer < 2; ++layer) {
                 if (a.flags & 1) mbar_wait_spin(dfull, nd & 1); else mbar_wait(dfull, nd & 1);
                 ++nd;
                 tc_fence_after();
@@ -532,14 +589,17 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
             if (dbg && q < 16 * nslot) dbg[(q / nslot) * 16 + 12] = clock64();
             const unsigned gp0 = (unsigned)tile * (unsigned)G;    // first centroid of the tile
             const unsigned cloud0 = gp0 / (unsigned)a.m, p0 = gp0 - cloud0 * (unsigned)a.m;
+            // rep > 1 (c3 <= 64): this warp's lanes hold copy cp of the channels and serve the columns [col0, col0 + ncol)
+            const int cp = (quad * 32) / L.c3r, chq = (quad * 32) % L.c3r;
+            const int ncol = TILE_M / L.rep, col0 = cp * ncol;
 #pragma unroll 1
             for (int j = 0; j < L.nb3; ++j) {
-                if (j * 128 + quad * 32 >= L.c3) continue;        // warp-uniform: these 32 lanes hold padding channels only
-                const int ch = j * 128 + row;
+                if (j * 128 + chq >= L.c3) continue;              // warp-uniform: these 32 lanes hold padding channels only
+                const int ch = j * 128 + chq + lane;
                 const float bias = ch < L.c3 ? b3[ch] : 0.f;
                 float run = -INFINITY;
 #pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {                   // 32 positions at a time
+                for (int cc = col0 >> 5; cc < ((col0 + ncol) >> 5); ++cc) {      // 32 positions at a time
                     uint32_t v[32];
                     tmem_ld32_raw(taddr + j * 128 + 32 * cc, v);
                     tmem_ld_wait<32>(v);
@@ -651,9 +711,15 @@ G4D_API int g4d_sa_mlp_pack_params(const g4d_sa_mlp_desc* d, const float* w1, co
         ok &= put_canonical(W2, L.c2, o, L.c1 + 1, b2[o] - bh);
     }
     __half* W3 = (__half*)(out + L.off_w3);
-    for (int o = 0; o < L.c3; ++o)
-        for (int k = 0; k < L.c2; ++k) ok &= put_canonical(W3, L.c3p, o, k, w3[(size_t)o * L.c2 + k]);
+    for (int cp = 0; cp < L.rep; ++cp)                            // rep > 1: copies of the channels down the 128 lanes (see make_layout)
+        for (int o = 0; o < L.c3; ++o)
+            for (int k = 0; k < L.c2; ++k) ok &= put_canonical(W3, L.c3p, cp * L.c3r + o, k, w3[(size_t)o * L.c2 + k]);
     memcpy(out + L.off_b3, b3, sizeof(float) * L.c3);
+    float* w1f = (float*)(out + L.off_w1f);                       // fp32 layer 1 for xyz-only levels (CUDA cores, in the producers)
+    for (int o = 0; o < L.c1 && cin == 0; ++o) {
+        for (int j = 0; j < 3; ++j) w1f[4 * o + j] = w1[(size_t)o * ld1 + j];
+        w1f[4 * o + 3] = b1[o];
+    }
     __half* ones = (__half*)(out + L.off_ones);
     for (int r = 0; r < TILE_M; ++r) { put_canonical(ones, TILE_M, r, 0, 1.f); put_canonical(ones, TILE_M, r, 1, 1.f); }
     if (!ok) return bad_arg("sa_mlp_pack_params: a folded weight or bias is outside the fp16 range (|v| > 65504)");

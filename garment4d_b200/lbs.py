@@ -87,9 +87,16 @@ def vertices2jointsB(J_regressor_B: Tensor, vertices: Tensor) -> Tensor:
 
 
 def blend_shapes(betas: Tensor, shape_disps: Tensor) -> Tensor:
-    """betas (B,NB), shape_disps (V,3,NB) -> (B,V,3) displacement (lbs.py:288-309).  A plain small GEMM: left to cuBLAS."""
+    """betas (B,NB), shape_disps (V,3,NB) -> (B,V,3) displacement (lbs.py:288-309)."""
     _need_cuda(betas, shape_disps)
-    return torch.einsum("bl,mkl->bmk", [betas, shape_disps])
+    if _wants_grad(betas, shape_disps):
+        return torch.einsum("bl,mkl->bmk", [betas, shape_disps])
+    bt, sd = _c(betas), _c(shape_disps)
+    B, NB = bt.shape
+    V = sd.shape[0]
+    out = torch.empty(B, V, 3, dtype=torch.float32, device=bt.device)
+    _lib.check(_lib.lib().g4d_blend_shapes(B, V, NB, _lib.ptr(bt), _lib.ptr(sd), _lib.ptr(out), _lib.stream_ptr()), "g4d_blend_shapes")
+    return out
 
 
 def transform_mat(R: Tensor, t: Tensor) -> Tensor:

@@ -215,6 +215,8 @@ int g4d_bias_relu_pm(int b, int c, int n, float* y, const float* bias, int relu,
 
 /* batch_rodrigues (lbs.py:312-346): rot_vecs (n,3) -> rot_mats (n,3,3) */
 int g4d_batch_rodrigues(int n, const float* rot_vecs, float* rot_mats, void* stream);
+/* blend_shapes (smplx/smplx/lbs.py:288-309): betas (F,NB), shape_disps (V,3,NB) -> out (F,V,3) displacements */
+int g4d_blend_shapes(int F, int V, int NB, const float* betas, const float* shape_disps, float* out, void* stream);
 /* vertices2joints / vertices2jointsB (lbs.py:251-286): J_regressor (J,V) or, per_frame_regressor=1, (F,J,V) */
 int g4d_vertices2joints(int F, int V, int J, int per_frame_regressor, const float* J_regressor, const float* vertices,
                         float* joints, void* stream);

@@ -16,6 +16,14 @@ if [ ! -d "$REF" ]; then
     exit 0
 fi
 mkdir -p "$OUT"
+# The reference's own Python operator layer (pointnet2_utils.py, pointnet2_modules.py, pytorch_utils.py), unmodified, next to its
+# kernels: tests/test_reference_layer_gpu.py imports it ON TOP OF the repository's pointnet2_cuda.py to show the drop-in boundary
+# holds (the GPU box has no /root/reference; like the .so, this copy is test infrastructure, git-ignored, never part of the product).
+mkdir -p "$OUT/pointnet2"
+for f in __init__.py pointnet2_utils.py pointnet2_modules.py pytorch_utils.py; do
+    [ -f "$REF/../$f" ] && cp -f "$REF/../$f" "$OUT/pointnet2/$f" && chmod u+w "$OUT/pointnet2/$f"
+done
+[ -f "$OUT/pointnet2/__init__.py" ] || : > "$OUT/pointnet2/__init__.py"
 if [ "$OUT/libpointnet2_ref.so" -nt "$HERE/ref_shim.cu" ] && [ "${1:-}" != "--force" ]; then
     echo "build_ref.sh: $OUT/libpointnet2_ref.so up to date"; exit 0
 fi

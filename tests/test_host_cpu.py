@@ -132,7 +132,7 @@ def test_sa_mlp_param_packing_layout():
     assert d.k0 == 32
     nbytes = L.g4d_sa_mlp_param_bytes(ctypes.byref(d))
     c3p = 128
-    assert nbytes == 2 * (d.k0 * c1 + (c1 + 16) * c2 + c2 * c3p) + 4 * c3p + 128 * 16 * 2
+    assert nbytes == 2 * (d.k0 * c1 + (c1 + 16) * c2 + c2 * c3p) + 4 * c3p + 128 * 16 * 2        # (+ 16 * c1 for xyz-only levels)
     rs = np.random.RandomState(0)
     w1, w2, w3 = (rs.randn(c1, 3 + c_in).astype(np.float32), rs.randn(c2, c1).astype(np.float32), rs.randn(c3, c2).astype(np.float32))
     b1, b2, b3 = (rs.randn(c).astype(np.float32) for c in (c1, c2, c3))
@@ -157,11 +157,22 @@ def test_sa_mlp_param_packing_layout():
     assert np.array_equal(W2[:, :c1], h(w2))
     assert np.array_equal(W2[:, c1], h(b2)) and np.abs(W2[:, c1] + W2[:, c1 + 1] - b2).max() < 2e-6 and not W2[:, c1 + 2:].any()
     W3, o = canon(o, c3p, c2)
-    assert np.array_equal(W3[:c3], h(w3)) and not W3[c3:].any()
+    # c3 = 40 <= 64 and nsample = 16 <= 64: W3 is replicated twice down the 128 lanes (rows 0.. and 64..), zero padding between
+    assert np.array_equal(W3[:c3], h(w3)) and np.array_equal(W3[64:64 + c3], h(w3)) and not W3[c3:64].any() and not W3[64 + c3:].any()
     assert np.array_equal(blob[o:o + 4 * c3].view(np.float32), b3)
     o += 4 * c3p
     ones, o = canon(o, 128, 16)
-    assert (ones[:, :2] == 1).all() and not ones[:, 2:].any() and o == nbytes
+    assert (ones[:, :2] == 1).all() and not ones[:, 2:].any()
+    assert o == nbytes
+    # xyz-only level: the fp32 layer-1 weights (wx, wy, wz, b) ride behind the ones operand (layer 1 runs on CUDA cores)
+    d0 = _lib.SaMlpDesc(0, c1, c2, c3, K, L.g4d_sa_mlp_k0(0))
+    n0 = L.g4d_sa_mlp_param_bytes(ctypes.byref(d0))
+    assert n0 == 2 * (d0.k0 * c1 + (c1 + 16) * c2 + c2 * c3p) + 4 * c3p + 128 * 16 * 2 + 16 * c1
+    blob0 = np.zeros(n0, np.uint8)
+    w1x = np.ascontiguousarray(w1[:, :3])
+    assert L.g4d_sa_mlp_pack_params(ctypes.byref(d0), *(a.ctypes.data for a in (w1x, b1, w2, b2, w3, b3)), blob0.ctypes.data) == 0
+    w1f = blob0[n0 - 16 * c1:].view(np.float32).reshape(c1, 4)
+    assert np.array_equal(w1f[:, :3], w1x) and np.array_equal(w1f[:, 3], b1)
     bad = _lib.SaMlpDesc(c_in, 20, c2, c3, K, d.k0)
     assert L.g4d_sa_mlp_param_bytes(ctypes.byref(bad)) == 0 and b"multiples of 16" in L.g4d_last_error()
     # a folded weight or bias outside the fp16 range is refused (the caller then takes the operator route)

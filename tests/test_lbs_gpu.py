@@ -103,3 +103,17 @@ def test_lbs_rejects_cpu_tensors():
     with pytest.raises(G4DError):
         glbs.lbs(torch.from_numpy(b), torch.from_numpy(p), *[torch.from_numpy(np.asarray(m[k])) for k in
                  ("v_template", "shapedirs", "posedirs", "J_regressor", "parents", "lbs_weights")])
+
+
+def test_blend_shapes_kernel(cuda):
+    """Stand-alone blend_shapes (lbs.py:288-309) on its own kernel vs the einsum it replaces (fp64 reference)."""
+    rs = np.random.RandomState(5)
+    for F, V, NB in ((1, 6890, 10), (7, 513, 10), (64, 100, 16)):
+        betas = rs.randn(F, NB).astype(np.float32)
+        sd = (rs.randn(V, 3, NB) * 0.01).astype(np.float32)
+        got = glbs.blend_shapes(torch.from_numpy(betas).to(cuda), torch.from_numpy(sd).to(cuda))
+        want = np.einsum("bl,mkl->bmk", betas.astype(np.float64), sd.astype(np.float64))
+        assert got.shape == (F, V, 3) and np.abs(got.cpu().numpy() - want).max() <= 1e-6
+    # the autograd route (einsum) gives the same values
+    b = torch.from_numpy(betas).to(cuda).requires_grad_(True)
+    assert torch.allclose(glbs.blend_shapes(b, torch.from_numpy(sd).to(cuda)), got, atol=1e-6)

@@ -375,3 +375,26 @@ def test_fp_batched_gemm_route_entry_points(cuda):
             _lib.check(L.g4d_bias_relu_unpack(Bq, Cq, nq, _lib.ptr(yin), in_half, _lib.ptr(bq), 1, _lib.ptr(out2), None,
                                               _lib.stream_ptr()), "g4d_bias_relu_unpack")
             assert torch.equal(out2, want)
+
+
+def test_group_all_equals_the_reference_views(cuda):
+    """GroupAll.forward (pointnet2_utils.py:273-291): (B, 3+C, 1, N) = cat(xyz^T, features) -- no kernel, torch views."""
+    rs = np.random.RandomState(3)
+    xyz = rs.rand(2, 77, 3).astype(np.float32)
+    feats = rs.randn(2, 5, 77).astype(np.float32)
+    x, f = _t(xyz, cuda), _t(feats, cuda)
+    out = pu.GroupAll(use_xyz=True)(x, None, f)
+    want = np.concatenate([xyz.transpose(0, 2, 1)[:, :, None, :], feats[:, :, None, :]], axis=1)
+    assert out.shape == (2, 8, 1, 77) and np.array_equal(out.cpu().numpy(), want)
+    assert np.array_equal(pu.GroupAll(use_xyz=False)(x, None, f).cpu().numpy(), feats[:, :, None, :])
+    assert np.array_equal(pu.GroupAll()(x, None, None).cpu().numpy(), xyz.transpose(0, 2, 1)[:, :, None, :])
+    # and through a set-abstraction module with npoint=None (PointnetSAModule, pointnet2_modules.py:94-113): operator route
+    from garment4d_b200.pointnet2 import pointnet2_modules as pm
+    torch.manual_seed(0)
+    sa = pm.PointnetSAModule(mlp=[5, 16, 32], use_xyz=True).to(cuda).eval()
+    with torch.no_grad():
+        new_xyz, y = sa(x, f)
+    assert new_xyz is None and y.shape == (2, 32, 1)
+    with torch.no_grad():
+        ref = torch.nn.functional.max_pool2d(sa.mlps[0](torch.from_numpy(want).to(cuda)), kernel_size=[1, 77]).squeeze(-1)
+    assert torch.allclose(y, ref)

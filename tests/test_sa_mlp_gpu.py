@@ -98,7 +98,7 @@ def test_training_mode_uses_operator_route_and_backprops(cuda):
     assert all(p.grad is not None for p in mod.parameters())
 
 
-@pytest.mark.parametrize("N", [2048, 1000])
+@pytest.mark.parametrize("N", [2048, 1000, 8192])
 def test_fused_fp0_head_vs_modules(cuda, N):
     """Encoder forward with the fused FP0+head kernel vs the module-by-module route (cuDNN, true fp32)."""
     from garment4d_b200.encoder import Pointnet2MSGSEG
@@ -201,6 +201,40 @@ def test_runner_host_path_equals_device_path(cuda, graphed):
     torch.cuda.synchronize()
     with torch.no_grad():
         _, sem_one, _, _ = model(pc)          # one big call: chunking must not change anything (every kernel works per cloud)
+    assert torch.equal(sem, sem_one)
+    assert torch.equal(lab, sem.argmax(dim=2).to(torch.uint8).cpu())
+    assert torch.equal(verts, v.cpu()) and torch.equal(joints, j.cpu())
+
+
+def test_graphed_runner_at_c3_size_equals_one_call(cuda):
+    """The benchmarked configuration itself: 240 frames x 8192 points, 4 frame groups, one captured CUDA graph -- identical
+    logits to ONE eager call over all frames, and the label map of the end-to-end (pinned host) graph equals their arg-max."""
+    from garment4d_b200 import synthetic
+    from garment4d_b200.encoder import Pointnet2MSGSEG
+    from garment4d_b200.runner import GraphedEncoderLBSRunner
+    import bench
+    torch.manual_seed(7)
+    model = Pointnet2MSGSEG(input_channels=0, bn=True, global_feat=False).to(cuda).eval()
+    smpl_np = synthetic.synthetic_smpl(seed=3)
+    smpl = [torch.from_numpy(np.ascontiguousarray(smpl_np[k])).to(cuda) for k in
+            ("v_template", "shapedirs", "posedirs", "J_regressor", "parents", "lbs_weights")]
+    C, N = 240, 8192
+    pc_pin = torch.from_numpy(bench.make_inputs("body", 99, C, N)).pin_memory()
+    b_np, p_np = synthetic.synthetic_frames(C, seed=4)
+    betas_pin, pose_pin = torch.from_numpy(b_np).pin_memory(), torch.from_numpy(p_np).pin_memory()
+    V = smpl[0].shape[0]
+    lab = torch.zeros(C, N, dtype=torch.uint8).pin_memory()
+    verts = torch.zeros(C, V, 3).pin_memory()
+    joints = torch.zeros(C, 24, 3).pin_memory()
+    pc, betas, pose = pc_pin.to(cuda), betas_pin.to(cuda), pose_pin.to(cuda)
+    r = GraphedEncoderLBSRunner(model, smpl, chunks=4, device=cuda)
+    r.capture(pc, betas, pose)
+    sem, v, j = r.replay_device()
+    r.capture_host(pc_pin, betas_pin, pose_pin, lab, verts, joints)
+    r.replay_host()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        _, sem_one, _, _ = model(pc)
     assert torch.equal(sem, sem_one)
     assert torch.equal(lab, sem.argmax(dim=2).to(torch.uint8).cpu())
     assert torch.equal(verts, v.cpu()) and torch.equal(joints, j.cpu())
