@@ -19,6 +19,11 @@ class SaMlpDesc(ctypes.Structure):
     _fields_ = [("c_in", _i), ("c1", _i), ("c2", _i), ("c3", _i), ("nsample", _i), ("k0", _i)]
 
 
+class Mlp2Desc(ctypes.Structure):
+    """struct g4d_mlp2_desc"""
+    _fields_ = [("c_in", _i), ("c1", _i), ("c2", _i)]
+
+
 class FpDesc(ctypes.Structure):
     """struct g4d_fp_desc"""
     _fields_ = [("c_in", _i), ("c1", _i), ("c2", _i), ("h1", _i), ("h2", _i)]
@@ -59,6 +64,9 @@ _SIGNATURES = {
     "g4d_fp_param_bytes": (_sz, [ctypes.POINTER(FpDesc)]),
     "g4d_fp_pack_params": (_i, [ctypes.POINTER(FpDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_fp_interp_mlp": (_i, [ctypes.POINTER(FpDesc), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_mlp2_param_bytes": (_sz, [ctypes.POINTER(Mlp2Desc)]),
+    "g4d_mlp2_pack_params": (_i, [ctypes.POINTER(Mlp2Desc), _vp, _vp, _vp, _vp, _vp]),
+    "g4d_mlp2_rows": (_i, [ctypes.POINTER(Mlp2Desc), _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "g4d_bias_relu_inplace": (_i, [_i, _i, ctypes.c_longlong, _vp, _vp, _i, _vp]),
     "g4d_fp_interp_concat": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_fp_interp_concat_cbn_h": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -69,6 +77,7 @@ _SIGNATURES = {
     "g4d_bias_relu_h": (_i, [_i, ctypes.c_longlong, _vp, _vp, _i, _vp]),
     "g4d_bias_relu_unpack": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "g4d_bias_relu_pm": (_i, [_i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "g4d_select_points": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_batch_rodrigues": (_i, [_i, _vp, _vp, _vp]),
     "g4d_blend_shapes": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "g4d_vertices2joints": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -25,9 +25,37 @@ from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
 
-# Feature-propagation MLPs in eval mode: "half" = one fp16 library GEMM per layer over the whole batch (default),
-# "conv" = per-cloud fp32/TF32 library convolution.  Both with our prologue / bias+ReLU epilogue kernels.
-_FP_GEMM = os.environ.get("G4D_FP_GEMM", "half")
+# Feature-propagation MLPs in eval mode: "tc" (default) = our two-layer tcgen05 kernel with streamed weights (g4d_mlp2_rows) on the
+# point-major rows our prologue kernel writes -- no library GEMM; shapes it does not take fall through to "half" = one fp16
+# library GEMM per layer over the whole batch with our bias+ReLU epilogues; "conv" = per-cloud fp32/TF32 library convolution.
+_FP_GEMM = os.environ.get("G4D_FP_GEMM", "tc")
+
+
+class _Mlp2Params:
+    """Device-resident packed parameters of a 2-layer folded MLP for g4d_mlp2_rows (None-able: see mlp2_supported)."""
+
+    def __init__(self, layers, device):
+        (w1, b1), (w2, b2) = [(w.detach().float().cpu().contiguous(), b.detach().float().cpu().contiguous()) for w, b in layers]
+        L = _lib.lib()
+        self.desc = _lib.Mlp2Desc(w1.shape[1], w1.shape[0], w2.shape[0])
+        nbytes = L.g4d_mlp2_param_bytes(ctypes.byref(self.desc))
+        if nbytes == 0:
+            raise _lib.G4DError("g4d_mlp2_param_bytes: " + L.g4d_last_error().decode())
+        blob = torch.empty(nbytes, dtype=torch.uint8)
+        rc = L.g4d_mlp2_pack_params(ctypes.byref(self.desc), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), blob.data_ptr())
+        _lib.check(rc, "g4d_mlp2_pack_params")
+        self.params = blob.to(device)
+        torch.cuda.current_stream(device).synchronize()      # other streams may run this module next: the blob must have landed
+        self.c_out = w2.shape[0]
+
+
+def mlp2_supported(layers):
+    if layers is None or len(layers) != 2:
+        return False
+    (w1, _), (w2, _) = layers
+    c1, c_in = w1.shape
+    c2 = w2.shape[0]
+    return c_in % 32 == 0 and c_in >= 32 and c1 % 64 == 0 and 64 <= c1 <= 512 and c2 % 64 == 0 and 64 <= c2 <= 256
 
 
 def _as_point_major_half(features: torch.Tensor) -> torch.Tensor:
@@ -37,6 +65,10 @@ def _as_point_major_half(features: torch.Tensor) -> torch.Tensor:
     if pm is not None:
         return pm
     return features.detach().transpose(1, 2).to(torch.float16).contiguous()
+
+
+def _FP_GEMM_NOW():
+    return _FP_GEMM          # module attribute: the tests switch routes by assigning it
 
 
 class _FusedBranch:
@@ -229,7 +261,7 @@ class PointnetFPModule(nn.Module):
             dist2 = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
             idx = torch.empty(B, n, 3, dtype=torch.int32, device=dev)
             pointnet2_utils.three_nn_raw(unknown, known, dist2, idx)
-            if _FP_GEMM == "half" and folded["half"] is not None and (B * n) % 8 == 0 and B <= 65535:
+            if _FP_GEMM_NOW() in ("half", "tc") and folded["half"] is not None and (B * n) % 8 == 0 and B <= 65535:
                 # The module's 1x1 convolutions as ONE library GEMM per layer over the whole batch: the concatenated input is
                 # written fp16 in (C, B*n) layout, hidden layers stay fp16 (fp32 accumulation; same 11-bit operand precision
                 # as the TF32 convolutions torch runs by default), bias+ReLU passes are ours, the last layer's GEMM returns
@@ -245,6 +277,17 @@ class PointnetFPModule(nn.Module):
                     rc = L.g4d_fp_interp_concat_rows_h(B, c2, c1, m, n, _lib.ptr(dist2), _lib.ptr(idx), _lib.ptr(kpm), _lib.ptr(spm),
                                                        _lib.ptr(x), _lib.stream_ptr())
                     _lib.check(rc, "g4d_fp_interp_concat_rows_h")
+                    tc = folded.get("tc") if _FP_GEMM_NOW() == "tc" else None
+                    if tc is not None:
+                        # both 1x1 convolutions + bias + ReLU in ONE tcgen05 kernel, weights streamed through shared memory
+                        out = torch.empty(B, tc.c_out, n, dtype=torch.float32, device=dev)
+                        pm = torch.empty(B, n, tc.c_out, dtype=torch.float16, device=dev) if self.emit_point_major else None
+                        rc = L.g4d_mlp2_rows(ctypes.byref(tc.desc), _lib.ptr(tc.params), B, n, _lib.ptr(x), _lib.ptr(out), _lib.ptr(pm),
+                                             _lib.stream_ptr())
+                        _lib.check(rc, "g4d_mlp2_rows")
+                        if pm is not None:
+                            pointnet2_utils.attach_point_major(out, pm)
+                        return out
                     for li, (w16, b) in enumerate(layers):
                         if li < len(layers) - 1:
                             x = F.linear(x, w16)
@@ -339,6 +382,13 @@ class PointnetFPModule(nn.Module):
                 half = [(w.to(torch.float16).contiguous(), b) for w, b in f]
                 if not all(bool(torch.isfinite(w).all()) for w, _ in half):     # folded weight outside the fp16 range: keep fp32
                     half = None
-                hit = (ver, {"conv": [(w[:, :, None, None].contiguous(), b) for w, b in f], "half": half})
+                tc = None
+                if half is not None and x.is_cuda and mlp2_supported(f):
+                    tc = _Mlp2Params(f, x.device)           # (packed on the host, synchronised: safe to use from any stream)
+                hit = (ver, {"conv": [(w[:, :, None, None].contiguous(), b) for w, b in f], "half": half, "tc": tc})
             self._fold_cache = hit
+            if x.is_cuda:
+                # the folded tensors were produced by asynchronous ops on THIS stream; the runner calls the module from several
+                # streams: wait until they exist before any other stream may pick them up from the cache
+                torch.cuda.current_stream(x.device).synchronize()
         return hit[1]

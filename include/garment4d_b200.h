@@ -213,6 +213,30 @@ int g4d_bias_relu_pm(int b, int c, int n, float* y, const float* bias, int relu,
 
 /* ---- 3. SMPL linear-blend skinning (smplx/smplx/lbs.py) ----------------------------------------- */
 
+/* Two-layer 1x1-conv MLP (eval BN folded, ReLU after both) over point-major fp16 rows on tcgen05 with the weights streamed
+ * through a shared-memory ring -- the MLPs of the coarser PointnetFPModule levels (pointnet2_modules.py:138-156, widths
+ * pointnet2encoder.py:91-96).  x (b*n, c_in) fp16 row-major (g4d_fp_interp_concat_rows_h) -> out_cm (b, c2, n) fp32 and,
+ * when out_pm != NULL, (b, n, c2) fp16 point-major. */
+typedef struct g4d_mlp2_desc {
+    int c_in;          /* multiple of 32                                   */
+    int c1;            /* hidden width, multiple of 32 in [64, 512]        */
+    int c2;            /* output width, multiple of 16 in [16, 256]        */
+} g4d_mlp2_desc;
+size_t g4d_mlp2_param_bytes(const g4d_mlp2_desc* d);
+/* w1 (c1, c_in), w2 (c2, c1): folded fp32 weights; fails ("fp16 range") when one does not fit fp16 */
+int g4d_mlp2_pack_params(const g4d_mlp2_desc* d, const float* w1, const float* b1, const float* w2, const float* b2, void* blob);
+int g4d_mlp2_rows(const g4d_mlp2_desc* d, const void* params_dev, int b, int n, const void* x_h, float* out_cm, void* out_pm,
+                  void* stream);
+
+/* ---- callers of the hot path inside the garment model ----
+ * Garment point selection (PCAGarmentEncoderSeg.calc_segmentation_results, modules/mesh_encoder.py:109-125): per frame the
+ * points whose arg-max class equals `target`, in their original order, the first n_out of them, zero-padded.
+ * sem_logits (c, n, ncls) fp32, or NULL with labels (c, n) uint8 given; xyz (c, n, 3); features (c, cf, n) channel-major or NULL
+ * (cf = 0) -> out_xyz (c, n_out, 3), out_feat (c, n_out, cf) point-major, out_count (c) = selected points before clipping
+ * (may be NULL). */
+int g4d_select_points(int c, int n, int ncls, int cf, int target, int n_out, const float* sem_logits, const unsigned char* labels,
+                      const float* xyz, const float* features, float* out_xyz, float* out_feat, int* out_count, void* stream);
+
 /* batch_rodrigues (lbs.py:312-346): rot_vecs (n,3) -> rot_mats (n,3,3) */
 int g4d_batch_rodrigues(int n, const float* rot_vecs, float* rot_mats, void* stream);
 /* blend_shapes (smplx/smplx/lbs.py:288-309): betas (F,NB), shape_disps (V,3,NB) -> out (F,V,3) displacements */

@@ -150,11 +150,11 @@ def test_fp_module_eval_routes_vs_operator_sequence(cuda, spec):
     finally:
         torch.backends.cudnn.allow_tf32 = old
     with torch.no_grad():
-        for route in ("half", "half+pm", "conv"):
+        for route in ("half", "half+pm", "tc+pm", "conv"):
             prev, pm._FP_GEMM = pm._FP_GEMM, route.split("+")[0]
             kin = kf.clone()
             sin = None if skip is None else skip.clone()
-            if route == "half+pm" and c2 % 8 == 0:      # features with the fp16 point-major copies the fused levels attach
+            if route.endswith("+pm") and c2 % 8 == 0:      # features with the fp16 point-major copies the fused levels attach
                 pu.attach_point_major(kin, kin.transpose(1, 2).to(torch.float16).contiguous())
                 if sin is not None:
                     pu.attach_point_major(sin, sin.transpose(1, 2).to(torch.float16).contiguous())       # -> the point-major rows route
