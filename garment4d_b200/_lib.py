@@ -78,6 +78,7 @@ _SIGNATURES = {
     "g4d_bias_relu_unpack": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "g4d_bias_relu_pm": (_i, [_i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "g4d_select_points": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_pe_mlp_max": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_batch_rodrigues": (_i, [_i, _vp, _vp, _vp]),
     "g4d_blend_shapes": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "g4d_vertices2joints": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -73,6 +73,108 @@ select_points_kernel(int n, int ncls, int cf, int target, int n_out, const float
         for (size_t e = (size_t)filled * cf + tid; e < (size_t)n_out * cf; e += SEL_THREADS) out_feat[e] = 0.f;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// g4d_pe_mlp_max -- one "positional encoding" unit of the GCN refinement (PCALBSGarmentUseSegEncoderSeg.forward,
+// modules/mesh_encoder.py:450-466):
+//     QueryAndGroup(xyz, new_xyz, features) (B, 3+C, P, K) -> permute -> Linear(3+C, H) -> ReLU -> Linear(H, H) -> max over K
+// 18 of them run per step (6 x 3 iterations), with gradients.  The reference materialises the grouped tensor and the two
+// activations ((B, P, K, H) each); here one kernel reads idx (from our ball query), gathers, runs the two small layers in fp32
+// on the CUDA cores (the reference's Linear is true fp32: torch's matmul TF32 switch is off by default) and reduces over the
+// neighbourhood, writing (B, P, H) and, for the backward pass, the arg-max sample of every channel.
+//   lane = one SAMPLE (32 / K centroids per warp): the lane streams its neighbour's fp32 feature row (point-major copy),
+//   keeps the H = 32 layer-1 accumulators in registers; weights are broadcast from shared memory (W^T, 128-bit loads:
+//   4 FMA per shared-memory instruction).
+constexpr int PE_H = 32;
+
+template <int K>
+__global__ void __launch_bounds__(256)
+pe_mlp_max_kernel(int n, int p, int c, const float* __restrict__ xyz_all, const float* __restrict__ new_xyz_all,
+                  const float* __restrict__ feat_pm_all, const int* __restrict__ idx_all, const float* __restrict__ w1t,
+                  const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
+                  float* __restrict__ out_all, signed char* __restrict__ arg_all) {
+    extern __shared__ __align__(16) float sw[];         // W1^T [(3+c)][32] | W2^T [32][32] | b1 [32] | b2 [32]
+    const int cin = 3 + c;
+    float* s_w1 = sw;
+    float* s_w2 = s_w1 + (size_t)cin * PE_H;
+    float* s_b1 = s_w2 + PE_H * PE_H;
+    float* s_b2 = s_b1 + PE_H;
+    for (int e = threadIdx.x; e < cin * PE_H; e += blockDim.x) s_w1[e] = __ldg(w1t + e);
+    for (int e = threadIdx.x; e < PE_H * PE_H; e += blockDim.x) s_w2[e] = __ldg(w2t + e);
+    if (threadIdx.x < PE_H) { s_b1[threadIdx.x] = __ldg(b1 + threadIdx.x); s_b2[threadIdx.x] = __ldg(b2 + threadIdx.x); }
+    __syncthreads();
+    constexpr int CPW = 32 / K;                          // centroids per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t cloud = blockIdx.y;
+    const int s = lane % K;
+    const unsigned gmask = K == 32 ? 0xFFFFFFFFu : (((1u << K) - 1u) << (lane / K * K));
+    const float* xyz = xyz_all + cloud * (size_t)n * 3;
+    const float* feat = feat_pm_all ? feat_pm_all + cloud * (size_t)n * c : nullptr;
+    for (int q0 = (blockIdx.x * (blockDim.x >> 5) + warp) * CPW; q0 < p; q0 += gridDim.x * (blockDim.x >> 5) * CPW) {
+        const int q = q0 + lane / K;
+        const bool live = q < p;
+        const int qs = live ? q : p - 1;
+        const int src = __ldg(idx_all + (cloud * p + qs) * K + s);
+        const float* nq = new_xyz_all + (cloud * p + qs) * 3;
+        float acc[PE_H];
+#pragma unroll
+        for (int j = 0; j < PE_H; ++j) acc[j] = s_b1[j];
+        {
+            const float x0 = __ldg(xyz + 3 * src) - __ldg(nq), x1 = __ldg(xyz + 3 * src + 1) - __ldg(nq + 1), x2 = __ldg(xyz + 3 * src + 2) - __ldg(nq + 2);
+#pragma unroll
+            for (int j4 = 0; j4 < PE_H / 4; ++j4) {
+                const float4 wa = *reinterpret_cast<const float4*>(s_w1 + 0 * PE_H + 4 * j4), wb = *reinterpret_cast<const float4*>(s_w1 + 1 * PE_H + 4 * j4),
+                             wc = *reinterpret_cast<const float4*>(s_w1 + 2 * PE_H + 4 * j4);
+                acc[4 * j4] = fmaf(x2, wc.x, fmaf(x1, wb.x, fmaf(x0, wa.x, acc[4 * j4])));
+                acc[4 * j4 + 1] = fmaf(x2, wc.y, fmaf(x1, wb.y, fmaf(x0, wa.y, acc[4 * j4 + 1])));
+                acc[4 * j4 + 2] = fmaf(x2, wc.z, fmaf(x1, wb.z, fmaf(x0, wa.z, acc[4 * j4 + 2])));
+                acc[4 * j4 + 3] = fmaf(x2, wc.w, fmaf(x1, wb.w, fmaf(x0, wa.w, acc[4 * j4 + 3])));
+            }
+        }
+        if (feat) {
+            const float* frow = feat + (size_t)src * c;
+            for (int i = 0; i < c; ++i) {                  // c is small for the body normals (3); rows are 16-byte aligned when c % 4 == 0
+                const float f = __ldg(frow + i);
+                const float* wr = s_w1 + (size_t)(3 + i) * PE_H;
+#pragma unroll
+                for (int j4 = 0; j4 < PE_H / 4; ++j4) {
+                    const float4 w = *reinterpret_cast<const float4*>(wr + 4 * j4);
+                    acc[4 * j4] = fmaf(f, w.x, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(f, w.y, acc[4 * j4 + 1]);
+                    acc[4 * j4 + 2] = fmaf(f, w.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(f, w.w, acc[4 * j4 + 3]);
+                }
+            }
+        }
+        float o[PE_H];
+#pragma unroll
+        for (int k = 0; k < PE_H; ++k) o[k] = s_b2[k];
+#pragma unroll
+        for (int j = 0; j < PE_H; ++j) {
+            const float h = fmaxf(acc[j], 0.f);
+#pragma unroll
+            for (int k4 = 0; k4 < PE_H / 4; ++k4) {
+                const float4 w = *reinterpret_cast<const float4*>(s_w2 + j * PE_H + 4 * k4);
+                o[4 * k4] = fmaf(h, w.x, o[4 * k4]); o[4 * k4 + 1] = fmaf(h, w.y, o[4 * k4 + 1]);
+                o[4 * k4 + 2] = fmaf(h, w.z, o[4 * k4 + 2]); o[4 * k4 + 3] = fmaf(h, w.w, o[4 * k4 + 3]);
+            }
+        }
+        // max over the K samples of the centroid (lanes of the group); the FIRST maximal sample is recorded for the backward pass
+        float* orow = out_all + (cloud * p + qs) * PE_H;
+        signed char* arow = arg_all ? arg_all + (cloud * p + qs) * PE_H : nullptr;
+#pragma unroll
+        for (int k = 0; k < PE_H; ++k) {
+            float m = o[k];
+#pragma unroll
+            for (int off = K / 2; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+            const unsigned eq = __ballot_sync(0xFFFFFFFFu, o[k] == m) & gmask;
+            if (live && s == 0) {
+                orow[k] = m;
+                if (arow) arow[k] = (signed char)(__ffs(eq) - 1 - (lane / K) * K);
+            }
+        }
+    }
+}
+
+
 }  // namespace g4d
 
 using namespace g4d;
@@ -86,4 +188,36 @@ G4D_API int g4d_select_points(int c, int n, int ncls, int cf, int target, int n_
     select_points_kernel<<<c, SEL_THREADS, 0, (cudaStream_t)stream>>>(n, ncls, cf, target, n_out, sem_logits, labels, xyz,
                                                                      cf > 0 ? features : nullptr, out_xyz, cf > 0 ? out_feat : nullptr, out_count);
     return finish_launch("g4d select_points");
+}
+
+// One positional-encoding unit (mesh_encoder.py:450-466).  xyz (b,n,3), new_xyz (b,p,3), feat_pm (b,n,c) fp32 POINT-major or NULL
+// (c = 0), idx (b,p,nsample) from the ball query (rows without a hit are all zero, as the reference leaves them), w1t (3+c, 32) =
+// Linear1.weight^T, b1 (32), w2t (32, 32) = Linear2.weight^T, b2 (32) -> out (b,p,32) fp32, argmax (b,p,32) int8 (may be NULL):
+// the sample that holds each channel's maximum.  nsample in {4, 8, 16, 32}.
+G4D_API int g4d_pe_mlp_max(int b, int n, int p, int c, int nsample, const float* xyz, const float* new_xyz, const float* feat_pm,
+                           const int* idx, const float* w1t, const float* b1, const float* w2t, const float* b2, float* out,
+                           signed char* argmax, void* stream) {
+    if (b < 0 || n <= 0 || p < 0 || c < 0) return bad_arg("pe_mlp_max: bad size");
+    if (b == 0 || p == 0) return 0;
+    if (!xyz || !new_xyz || !idx || !w1t || !b1 || !w2t || !b2 || !out || (c > 0 && !feat_pm)) return bad_arg("pe_mlp_max: null pointer");
+    if (b > 65535) return bad_arg("pe_mlp_max: b > 65535");
+    const size_t smem = ((size_t)(3 + c) * PE_H + PE_H * PE_H + 2 * PE_H) * sizeof(float);
+    if (smem > 200 * 1024) return bad_arg("pe_mlp_max: 3 + c too large for the shared-memory weight image");
+    cudaStream_t s = (cudaStream_t)stream;
+    int gx = (p + 7) / 8;                                 // 8 warps per CTA, >= 1 centroid per warp
+    if (gx > 148 * 4) gx = 148 * 4;
+    dim3 grid(gx, b);
+#define G4D_PE(KK) { \
+        cudaError_t e = cudaFuncSetAttribute(pe_mlp_max_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) { set_error("pe_mlp_max: shared memory opt-in: %s", cudaGetErrorString(e)); return (int)e; } \
+        pe_mlp_max_kernel<KK><<<grid, 256, smem, s>>>(n, p, c, xyz, new_xyz, c > 0 ? feat_pm : nullptr, idx, w1t, b1, w2t, b2, out, argmax); }
+    switch (nsample) {
+        case 4: G4D_PE(4) break;
+        case 8: G4D_PE(8) break;
+        case 16: G4D_PE(16) break;
+        case 32: G4D_PE(32) break;
+        default: return bad_arg("pe_mlp_max: nsample must be 4, 8, 16 or 32");
+    }
+#undef G4D_PE
+    return finish_launch("g4d pe_mlp_max");
 }

@@ -76,8 +76,15 @@ class _FusedBranch:
 
     def __init__(self, mlp: pt_utils.SharedMLP, nsample: int, c_in: int, device):
         folded = pt_utils.fold_shared_mlp(mlp)
-        assert folded is not None and len(folded) == 3
-        (w1, b1), (w2, b2), (w3, b3) = [(w.cpu().contiguous(), b.cpu().contiguous()) for w, b in folded]
+        assert folded is not None and len(folded) in (2, 3)
+        folded = [(w.cpu().contiguous(), b.cpu().contiguous()) for w, b in folded]
+        if len(folded) == 2:
+            # two-layer MLP (the garment encoder's branches, mesh_encoder.py:58-70) on the three-layer kernel: an identity middle
+            # layer is exact -- its input is post-ReLU fp16, the products 1*h accumulate exactly in fp32, ReLU and the rounding
+            # back to fp16 change nothing
+            c1 = folded[0][0].shape[0]
+            folded = [folded[0], (torch.eye(c1, dtype=torch.float32), torch.zeros(c1, dtype=torch.float32)), folded[1]]
+        (w1, b1), (w2, b2), (w3, b3) = folded
         assert w1.shape[1] == c_in + 3
         L = _lib.lib()
         self.desc = _lib.SaMlpDesc(c_in, w1.shape[0], w2.shape[0], w3.shape[0], nsample, L.g4d_sa_mlp_k0(c_in))
@@ -95,12 +102,13 @@ class _FusedBranch:
 def fused_branch_supported(mlp, grouper, c_in):
     if not isinstance(grouper, pointnet2_utils.QueryAndGroup) or not grouper.use_xyz:
         return False
-    if grouper.nsample not in (8, 16, 32, 64, 128) or c_in % 8 != 0 or len(mlp) != 3:
+    if grouper.nsample not in (8, 16, 32, 64, 128) or c_in % 8 != 0 or len(mlp) not in (2, 3):
         return False
     folded = pt_utils.fold_shared_mlp(mlp)
     if folded is None:
         return False
-    c1, c2, c3 = (w.shape[0] for w, _ in folded)
+    widths = [w.shape[0] for w, _ in folded]
+    c1, c2, c3 = widths if len(widths) == 3 else (widths[0], widths[0], widths[1])
     return c1 % 16 == 0 and c2 % 16 == 0 and 16 <= c1 <= 256 and 16 <= c2 <= 256 and c3 <= 256
 
 
@@ -140,9 +148,10 @@ class _PointnetSAModuleBase(nn.Module):
                 try:
                     br = _FusedBranch(self.mlps[i], self.groupers[i].nsample, c_in, device)
                 except _lib.G4DError as e:
-                    if "fp16 range" not in str(e):
+                    if "fp16 range" not in str(e) and "shared memory footprint" not in str(e):
                         raise
-                    br = None       # fp16 operands cannot hold these folded weights: operator route (fp32 / TF32 layers)
+                    br = None       # fp16 operands cannot hold these folded weights, or the resident weights do not fit shared
+                                    # memory (e.g. 256-wide two-layer branches): operator route (fp32 / TF32 layers)
             hit = (ver, br)
             self._fused_cache[key] = hit
         return hit[1]

@@ -237,6 +237,14 @@ int g4d_mlp2_rows(const g4d_mlp2_desc* d, const void* params_dev, int b, int n, 
 int g4d_select_points(int c, int n, int ncls, int cf, int target, int n_out, const float* sem_logits, const unsigned char* labels,
                       const float* xyz, const float* features, float* out_xyz, float* out_feat, int* out_count, void* stream);
 
+/* One positional-encoding unit of the GCN refinement (modules/mesh_encoder.py:450-466): QueryAndGroup -> Linear(3+c,32) -> ReLU ->
+ * Linear(32,32) -> max over the nsample neighbours, fp32, one kernel.  feat_pm (b,n,c) fp32 POINT-major (NULL with c = 0); idx
+ * (b,p,nsample) from the ball query; w1t (3+c,32), w2t (32,32): the Linear weights transposed -> out (b,p,32), argmax (b,p,32) int8
+ * (sample holding each maximum; may be NULL).  nsample in {4, 8, 16, 32}. */
+int g4d_pe_mlp_max(int b, int n, int p, int c, int nsample, const float* xyz, const float* new_xyz, const float* feat_pm,
+                   const int* idx, const float* w1t, const float* b1, const float* w2t, const float* b2, float* out,
+                   signed char* argmax, void* stream);
+
 /* batch_rodrigues (lbs.py:312-346): rot_vecs (n,3) -> rot_mats (n,3,3) */
 int g4d_batch_rodrigues(int n, const float* rot_vecs, float* rot_mats, void* stream);
 /* blend_shapes (smplx/smplx/lbs.py:288-309): betas (F,NB), shape_disps (V,3,NB) -> out (F,V,3) displacements */
