@@ -77,6 +77,9 @@ _SIGNATURES = {
     "g4d_bias_relu_h": (_i, [_i, ctypes.c_longlong, _vp, _vp, _i, _vp]),
     "g4d_bias_relu_unpack": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "g4d_bias_relu_pm": (_i, [_i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "g4d_scatter_det_workspace_bytes": (_sz, [_i, _i, _i]),
+    "g4d_scatter_det_build": (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    "g4d_scatter_det_apply": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4d_select_points": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_pe_mlp_max": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_batch_rodrigues": (_i, [_i, _vp, _vp, _vp]),

@@ -140,7 +140,7 @@ fp_mlp2_kernel(const Mlp2Args a) {
             for (int q = 0; q < nq; ++q)
                 for (int st = 0; st < per_tile; ++st, ++g) {
                     const uint32_t slot = g % NST, ph = (g / NST) & 1;
-                    mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);
+                    mbar_wait(bar_empty + 8 * slot, ph ^ 1);       // (suspending wait: a nanosleep poll costs >= 256 ns per miss, and with 2-4 stages nearly every wait misses)
                     const bool l1 = st < n1;
                     const uint32_t bytes = l1 ? L.w1_stage : L.w2_stage;
                     const unsigned char* src = a.blob + (l1 ? L.off_w1 + (size_t)st * L.w1_stage : L.off_w2 + (size_t)(st - n1) * L.w2_stage);
@@ -162,7 +162,7 @@ fp_mlp2_kernel(const Mlp2Args a) {
             const char* srow = reinterpret_cast<const char*>(a.x + (size_t)(live ? R : 0) * L.c_in);
             for (int st = 0; st < per_tile; ++st, ++g) {
                 const uint32_t slot = g % NST, ph = (g / NST) & 1;
-                mbar_wait_relaxed(bar_empty + 8 * slot, ph ^ 1);
+                mbar_wait(bar_empty + 8 * slot, ph ^ 1);       // (suspending wait: a nanosleep poll costs >= 256 ns per miss, and with 2-4 stages nearly every wait misses)
                 if (st < n1) {
                     const uint32_t sdst = s_ring + slot * L.stage_bytes + (uint32_t)r * 16;
 #pragma unroll

@@ -335,7 +335,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 const int sl = q_this % nslot, t = q_this / nslot; // slot and index of the tile within its slot
                 const int buf = t & 1;
                 const uint32_t hf = bar_hfree + 8 * (2 * sl + buf), h1f = bar_h1full + 8 * (2 * sl + buf);
-                mbar_wait_relaxed(hf, ((t >> 1) + 1) & 1);         // layer 3 of tile t-2 has read this buffer (passes at once for t < 2)
+                mbar_wait(hf, ((t >> 1) + 1) & 1);         // layer 3 of tile t-2 has read this buffer (passes at once for t < 2)
                 uint4* hd = reinterpret_cast<uint4*>(smem + L.off_h + (size_t)(2 * sl + buf) * L.h_bytes);
                 const float4* w1f = reinterpret_cast<const float4*>(smem + L.off_w1f);
 #pragma unroll 1
@@ -367,7 +367,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 const uint32_t slot_w = slot;
 #pragma unroll 1
                 for (int sl = w0; sl < w1; ++sl) {
-                    mbar_wait_relaxed(bar_empty + 8 * (rbase + slot), ph ^ 1);           // slot free (first lap passes at once)
+                    mbar_wait(bar_empty + 8 * (rbase + slot), ph ^ 1);           // slot free (first lap passes at once); suspending wait, not a nanosleep poll (>= 256 ns per miss)
                     const uint32_t sdst = s_ring + (rbase + slot) * SLICE_BYTES + (uint32_t)r * 16;
                     uint4* gdst = reinterpret_cast<uint4*>(smem + L.off_ring + (size_t)(rbase + slot) * SLICE_BYTES);
 #pragma unroll
@@ -552,6 +552,22 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 const int ncols = layer ? L.c2 : L.c1;
                 uint4* hd = reinterpret_cast<uint4*>(hbuf);
                 int c = 0;
+                if constexpr (!BIG) {
+                    // one-slot layout (13 warps, up to 157 registers): two TMEM loads in flight per wait -- the load -> wait ->
+                    // convert -> store chain of this warp is the tile's critical path (nothing else runs meanwhile)
+#pragma unroll 1
+                    for (; c + 64 <= ncols; c += 64) {
+                        uint32_t v[64];
+                        tmem_ld32_raw(taddr + c, v);
+                        tmem_ld32_raw(taddr + c + 32, v + 32);
+                        tmem_ld_wait<64>(v);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            hd[(size_t)((c >> 3) + u) * TILE_M + row] =
+                                make_uint4(pack_relu_bits(v[8 * u], v[8 * u + 1]), pack_relu_bits(v[8 * u + 2], v[8 * u + 3]),
+                                           pack_relu_bits(v[8 * u + 4], v[8 * u + 5]), pack_relu_bits(v[8 * u + 6], v[8 * u + 7]));
+                    }
+                }
 #pragma unroll 1
                 for (; c + 32 <= ncols; c += 32) {
                     uint32_t v[32];
@@ -598,6 +614,40 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                 const int ch = j * 128 + chq + lane;
                 const float bias = ch < L.c3 ? b3[ch] : 0.f;
                 float run = -INFINITY;
+                // CH positions per step: 32, or 64 with two TMEM loads in flight in the one-slot layout (when the copy spans >= 64)
+                constexpr int CHMAX = BIG ? 32 : 64;
+                if (CHMAX == 64 && (ncol & 63) == 0) {
+#pragma unroll 1
+                    for (int cc = col0 >> 6; cc < ((col0 + ncol) >> 6); ++cc) {
+                        uint32_t v[64];
+                        tmem_ld32_raw(taddr + j * 128 + 64 * cc, v);
+                        tmem_ld32_raw(taddr + j * 128 + 64 * cc + 32, v + 32);
+                        tmem_ld_wait<64>(v);
+                        constexpr int GPC = NS <= 64 ? 64 / NS : 1;
+                        constexpr int W = NS <= 64 ? NS : 64;
+#pragma unroll
+                        for (int g = 0; g < GPC; ++g) {
+                            float mx = __uint_as_float(v[W * g]);
+#pragma unroll
+                            for (int i = 1; i < W; ++i) mx = fmaxf(mx, __uint_as_float(v[W * g + i]));
+                            int gi;
+                            if constexpr (NS <= 64) { gi = cc * GPC + g; }
+                            else {
+                                run = fmaxf(run, mx);
+                                if (((cc + 1) * 64) % NS != 0) continue;
+                                mx = run; run = -INFINITY;
+                                gi = (cc * 64) / NS;
+                            }
+                            const unsigned gp = gp0 + (unsigned)gi;
+                            if (ch < L.c3 && (gp << LG_NS) < (unsigned)a.total_rows) {
+                                const float o = fmaxf(mx + bias, 0.f);
+                                if (staged) stage[ch * (G + 1) + gi] = o;
+                                else store_cm_direct(a.out_cm, cloud0, p0 + (unsigned)gi, (unsigned)a.m, a.ctot, a.coff + ch, o);
+                                if (a.out_pm) a.out_pm[(size_t)gp * a.ctot + a.coff + ch] = __float2half_rn(fminf(o, 65504.f));
+                            }
+                        }
+                    }
+                } else {
 #pragma unroll 1
                 for (int cc = col0 >> 5; cc < ((col0 + ncol) >> 5); ++cc) {      // 32 positions at a time
                     uint32_t v[32];
@@ -626,6 +676,7 @@ sa_mlp_max_kernel(const SaMlpArgs a) {
                             if (a.out_pm) a.out_pm[(size_t)gp * a.ctot + a.coff + ch] = __float2half_rn(fminf(o, 65504.f));
                         }
                     }
+                }
                 }
             }
             if (dbg && q < 16 * nslot) dbg[(q / nslot) * 16 + 15] = clock64();

@@ -75,6 +75,39 @@ def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
+# Backward kernels: "det" (default) = deterministic segmented reduction (scatter_det.cu); "atomic" = the reference's atomicAdd
+# scatters (1:1 entry points g4d_*_grad), whose result depends on the order the atomics land in.
+BACKWARD = os.environ.get("G4D_BACKWARD", "det")
+
+
+def scatter_add_deterministic(dst: torch.Tensor, n_dst: int, grad: torch.Tensor, weight: torch.Tensor = None, grad_div: int = 1) -> torch.Tensor:
+    """out[b, c, dst[b, e]] += weight[b, e] * grad[b, c, e // grad_div], summed in ascending e: the three backward scatters of the
+    reference (group / gather / three_interpolate) as one deterministic segmented reduction.  dst (B, n_src) int32 (any trailing
+    shape, flattened), grad (B, C, n_src // grad_div) fp32 -> (B, C, n_dst).  The index structure is cached on `dst`."""
+    B = dst.shape[0]
+    dflat = dst.reshape(B, -1)
+    n_src = dflat.shape[1]
+    C = grad.shape[1]
+    grad = grad.reshape(B, C, -1)
+    _chk(dflat, torch.int32, "dst"); _chk(grad, torch.float32, "grad")
+    if weight is not None:
+        weight = _chk(weight.reshape(B, -1), torch.float32, "weight")
+    L = _lib.lib()
+    hit = getattr(dst, "_g4d_csr", None)
+    if hit is None or hit[1] != dst._version or hit[2] != n_dst:
+        ws = torch.empty(L.g4d_scatter_det_workspace_bytes(B, n_src, n_dst) // 4, dtype=torch.int32, device=dst.device)
+        _lib.check(L.g4d_scatter_det_build(B, n_src, n_dst, _lib.ptr(dflat), _lib.ptr(ws), _lib.stream_ptr()), "g4d_scatter_det_build")
+        hit = (ws, dst._version, n_dst)
+        try:
+            dst._g4d_csr = hit
+        except Exception:
+            pass
+    out = torch.empty(B, C, n_dst, dtype=torch.float32, device=grad.device)
+    rc = L.g4d_scatter_det_apply(B, C, n_src, n_dst, grad_div, _lib.ptr(hit[0]), _lib.ptr(weight), _lib.ptr(grad), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "g4d_scatter_det_apply")
+    return out
+
+
 GRID_MIN_POINTS = 2048     # below this the brute-force scans are already cheap
 FPS_PRUNE_MIN_POINTS = 2048
 # "rows": Morton-ordered warp-row pruned kernel (fps_rows.cu, default); "pruned": the cell-sorted thread-per-clump kernel of
@@ -174,6 +207,8 @@ class GatherOperation(Function):
     def backward(ctx, grad_out):
         idx, C, N = ctx.for_backwards
         B, npoint = idx.size()
+        if BACKWARD == "det":
+            return scatter_add_deterministic(idx, N, grad_out.contiguous()), None
         grad_features = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
         pointnet2.gather_points_grad_wrapper(B, C, N, npoint, grad_out.contiguous(), idx, grad_features)
         return grad_features, None
@@ -239,6 +274,8 @@ class ThreeInterpolate(Function):
     def backward(ctx, grad_out: torch.Tensor):
         idx, weight, m = ctx.three_interpolate_for_backward
         B, c, n = grad_out.size()
+        if BACKWARD == "det":
+            return scatter_add_deterministic(idx, m, grad_out.contiguous(), weight=weight.contiguous(), grad_div=3), None, None
         grad_features = torch.zeros(B, c, m, dtype=torch.float32, device=grad_out.device)
         pointnet2.three_interpolate_grad_wrapper(B, c, n, m, grad_out.contiguous(), idx, weight, grad_features)
         return grad_features, None, None
@@ -264,6 +301,8 @@ class GroupingOperation(Function):
     def backward(ctx, grad_out: torch.Tensor):
         idx, N = ctx.for_backwards
         B, C, npoint, nsample = grad_out.size()
+        if BACKWARD == "det":
+            return scatter_add_deterministic(idx, N, grad_out.contiguous()), None
         grad_features = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
         pointnet2.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.contiguous(), idx, grad_features)
         return grad_features, None
@@ -366,16 +405,22 @@ class _QueryAndGroupFused(Function):
         if use_xyz:
             gx = grad_out[:, :3].contiguous()
             if ctx.needs_input_grad[3]:
-                g = torch.zeros(B, 3, N, dtype=torch.float32, device=grad_out.device)
-                pointnet2.group_points_grad_wrapper(B, 3, N, P, S, gx, idx, g)
+                if BACKWARD == "det":
+                    g = scatter_add_deterministic(idx, N, gx)
+                else:
+                    g = torch.zeros(B, 3, N, dtype=torch.float32, device=grad_out.device)
+                    pointnet2.group_points_grad_wrapper(B, 3, N, P, S, gx, idx, g)
                 g_xyz = g.transpose(1, 2).contiguous()
             if ctx.needs_input_grad[4]:
                 g_new = -gx.sum(dim=3).transpose(1, 2).contiguous()
             off = 3
         if C > 0 and ctx.needs_input_grad[5]:
             gf = grad_out[:, off:].contiguous()
-            g_feat = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
-            pointnet2.group_points_grad_wrapper(B, C, N, P, S, gf, idx, g_feat)
+            if BACKWARD == "det":
+                g_feat = scatter_add_deterministic(idx, N, gf)
+            else:
+                g_feat = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+                pointnet2.group_points_grad_wrapper(B, C, N, P, S, gf, idx, g_feat)
         return None, None, None, g_xyz, g_new, g_feat
 
 

@@ -228,6 +228,18 @@ int g4d_mlp2_pack_params(const g4d_mlp2_desc* d, const float* w1, const float* b
 int g4d_mlp2_rows(const g4d_mlp2_desc* d, const void* params_dev, int b, int n, const void* x_h, float* out_cm, void* out_pm,
                   void* stream);
 
+/* ---- deterministic backward ----
+ * The reference's three backward kernels (group_points_grad group_points_gpu.cu:8-25, gather_points_grad sampling_gpu.cu:46-63,
+ * three_interpolate_grad interpolate_gpu.cu:120-142) are atomicAdd scatters: out[b,c,dst[b,e]] += w[b,e] * grad[b,c,e].  These two
+ * calls compute the same sums as a segmented reduction in ascending source order: bit-identical from run to run.
+ * build: dst (b, n_src) int32 in [0, n_dst) -> index structure in workspace (g4d_scatter_det_workspace_bytes), reusable for any
+ * number of apply calls; apply: weight (b, n_src) or NULL (= 1), grad (b, c, n_src / grad_div) read at [e / grad_div] (grad_div = 3
+ * for three_interpolate, else 1) -> out (b, c, n_dst), every element written. */
+size_t g4d_scatter_det_workspace_bytes(int b, int n_src, int n_dst);
+int g4d_scatter_det_build(int b, int n_src, int n_dst, const int* dst, void* workspace, void* stream);
+int g4d_scatter_det_apply(int b, int c, int n_src, int n_dst, int grad_div, const void* workspace, const float* weight,
+                          const float* grad, float* out, void* stream);
+
 /* ---- callers of the hot path inside the garment model ----
  * Garment point selection (PCAGarmentEncoderSeg.calc_segmentation_results, modules/mesh_encoder.py:109-125): per frame the
  * points whose arg-max class equals `target`, in their original order, the first n_out of them, zero-padded.

@@ -128,6 +128,47 @@ def test_backward_ops_vs_oracle(cuda):
     np.testing.assert_allclose(feats3.grad.cpu().numpy(), orc.three_interpolate_grad(go3, iidx, w, m), rtol=1e-5, atol=1e-5)
 
 
+def test_deterministic_backward_is_bit_exact_and_reproducible(cuda):
+    """The segmented-reduction backward (scatter_det.cu) adds every destination's contributions in ascending source order:
+    bit-identical to the serial loop of the oracle (the reference's atomicAdd scatter has no defined order), run after run,
+    including the heavy-hitter case (all-zero idx rows of empty balls pile thousands of sources onto point 0)."""
+    assert pu.BACKWARD == "det"
+    rs = np.random.RandomState(5)
+    B, C, N, P, S = 3, 7, 2000, 700, 32
+    idx = rs.randint(0, N, (B, P, S)).astype(np.int32)
+    idx[:, 100:400] = 0                                          # 9600 sources on point 0 of every cloud
+    go = rs.randn(B, C, P, S).astype(np.float32)
+    want = orc.grouping_operation_grad(go, idx, N)
+    outs = []
+    for _ in range(3):
+        feats = torch.zeros(B, C, N, device=cuda, requires_grad=True)
+        pu.grouping_operation(feats, _t(idx, cuda)).backward(_t(go, cuda))
+        outs.append(feats.grad.clone())
+    assert np.array_equal(outs[0].cpu().numpy(), want)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    # gather and three_interpolate through the same primitive
+    gidx = rs.randint(0, N, (B, P)).astype(np.int32)
+    go2 = rs.randn(B, C, P).astype(np.float32)
+    f2 = torch.zeros(B, C, N, device=cuda, requires_grad=True)
+    pu.gather_operation(f2, _t(gidx, cuda)).backward(_t(go2, cuda))
+    assert np.array_equal(f2.grad.cpu().numpy(), orc.gather_operation_grad(go2, gidx, N))
+    m, n = 300, 5000
+    iidx = rs.randint(0, m, (B, n, 3)).astype(np.int32)
+    w = rs.rand(B, n, 3).astype(np.float32)
+    go3 = rs.randn(B, C, n).astype(np.float32)
+    f3 = torch.zeros(B, C, m, device=cuda, requires_grad=True)
+    pu.three_interpolate(f3, _t(iidx, cuda), _t(w, cuda)).backward(_t(go3, cuda))
+    assert np.array_equal(f3.grad.cpu().numpy(), orc.three_interpolate_grad(go3, iidx, w, m))
+    # the 1:1 atomic entry points (the reference's kernels' shape) agree up to summation order
+    prev, pu.BACKWARD = pu.BACKWARD, "atomic"
+    try:
+        fa = torch.zeros(B, C, N, device=cuda, requires_grad=True)
+        pu.grouping_operation(fa, _t(idx, cuda)).backward(_t(go, cuda))
+    finally:
+        pu.BACKWARD = prev
+    np.testing.assert_allclose(fa.grad.cpu().numpy(), want, rtol=1e-4, atol=1e-3)
+
+
 def test_query_and_group_backward_matches_composition(cuda):
     xyz = clouds(41, 2, 600, "cube")
     x = _t(xyz, cuda)

@@ -13,7 +13,9 @@ if [ "${SKIP_TESTS:-0}" != 1 ]; then
   timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> $OUT/${TAG}_smoke.log
   tail -2 $OUT/${TAG}_smoke.log
 fi
-timeout -k 10 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
+if [ "${SKIP_BENCH:-0}" != 1 ]; then
+timeout -k 10 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
+fi
 if [ "${SKIP_REF:-0}" != 1 ]; then
   timeout -k 10 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference.json 2>> $OUT/${TAG}_bench.err
 fi
@@ -32,8 +34,11 @@ if [ "${SKIP_NCU:-0}" != 1 ]; then
       -k regex:'g4d::fp_interp_mlp' -f -o $OUT/${TAG}_full_fp python tools/ncu_once.py c3 > $OUT/${TAG}_full_fp_run.log 2>&1
   echo "ncu fp_interp_mlp exit $?"
   # launch list of the bench command (device time per launch; cold-cache, serialised: shares, not absolutes)
+  # (one frame group / stream: with several streams the 216 KB feature-propagation kernel failed to launch under ncu)
   timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches.csv \
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-breakdown > $OUT/${TAG}_launches_run.log 2>&1
+      python bench.py --config c3 --chunks ${LAUNCH_CHUNKS:-1} --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-breakdown --no-train --no-extras > $OUT/${TAG}_launches_run.log 2>&1
   echo "ncu launches exit $?"
+  python tools/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.md 2>&1
+  gzip -f $OUT/${TAG}_launches.csv
 fi
 ls -la $OUT | tail -20
