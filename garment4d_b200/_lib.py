@@ -48,6 +48,7 @@ _SIGNATURES = {
     "g4d_ball_query2": (_i, [_i, _i, _i, _f, _i, _vp, _f, _i, _vp, _vp, _vp, _vp]),
     "g4d_query_and_group": (_i, [_i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_group_fused": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_group_fused_pm": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_grid_bytes": (_sz, [_i, _i]),
     "g4d_grid_build": (_i, [_i, _i, _vp, _f, _vp, _vp]),
     "g4d_fps_gather_grid": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),

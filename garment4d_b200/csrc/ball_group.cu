@@ -252,6 +252,59 @@ group_fused_kernel(int n, int m, int c, int K, int use_xyz, const float* __restr
     }
 }
 
+// Grouping stage of QueryAndGroup from POINT-MAJOR fp32 features (b, n, c): a neighbour's channels are one contiguous row, so the
+// gather moves 256-byte pieces (16 lanes x float4) instead of one 4-byte word per channel and lane, and the (b, 3+c, m, K) output
+// -- channel-major, 98 % of the traffic -- is written through a shared-memory transpose as 256-byte runs per channel.
+// (group_fused_kernel, reading the reference's channel-major layout directly, stalls on its scalar gathers at 41-47 % of DRAM
+// bandwidth: profiles/r01_ncu_summary.md.)  One CTA = 64 consecutive (centroid, sample) positions x all channels, 64 at a time.
+constexpr int GR_E = 64, GR_C = 64;
+__global__ void __launch_bounds__(256)
+group_rows_kernel(int n, int m, int c, int K, int use_xyz, const float* __restrict__ xyz_all, const float* __restrict__ new_xyz_all,
+                  const float* __restrict__ feat_pm_all, const int* __restrict__ idx_all, float* __restrict__ out_all) {
+    __shared__ int sidx[GR_E];
+    __shared__ float tile[GR_C][GR_E + 1];
+    const size_t cloud = blockIdx.y;
+    const size_t plane = (size_t)m * K;
+    const size_t e0 = (size_t)blockIdx.x * GR_E;
+    const int ne = (int)((plane - e0) < (size_t)GR_E ? (plane - e0) : (size_t)GR_E);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cxyz = use_xyz ? 3 : 0;
+    float* out = out_all + cloud * (size_t)(cxyz + c) * plane + e0;
+    if (tid < GR_E) sidx[tid] = tid < ne ? __ldg(idx_all + cloud * plane + e0 + tid) : 0;
+    __syncthreads();
+    if (use_xyz && tid < 3 * GR_E) {
+        const int d = tid / GR_E, e = tid - d * GR_E;           // lanes along e: coalesced plane writes
+        if (e < ne) {
+            const size_t q = (e0 + e) / K;
+            out[(size_t)d * plane + e] = __ldg(xyz_all + (cloud * n + sidx[e]) * 3 + d) - __ldg(new_xyz_all + (cloud * m + q) * 3 + d);
+        }
+    }
+    const float* feat = feat_pm_all + cloud * (size_t)n * c;
+    const int hl = lane & 15, hs = lane >> 4;                    // 16 lanes x float4 = one 64-channel piece of a row; two rows per warp load
+    for (int c0 = 0; c0 < c; c0 += GR_C) {
+        const int nc = (c - c0) < GR_C ? (c - c0) : GR_C;
+        // gather: warp w takes positions w, w+8, ... two at a time
+#pragma unroll 2
+        for (int e = 2 * warp + hs; e < GR_E; e += 16) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < ne && 4 * hl < nc) {
+                const float* row = feat + (size_t)sidx[e] * c + c0 + 4 * hl;
+                if (((c | c0) & 3) == 0 && 4 * hl + 3 < nc) v = __ldg(reinterpret_cast<const float4*>(row));
+                else { v.x = __ldg(row); if (4 * hl + 1 < nc) v.y = __ldg(row + 1); if (4 * hl + 2 < nc) v.z = __ldg(row + 2); if (4 * hl + 3 < nc) v.w = __ldg(row + 3); }
+            }
+            tile[4 * hl][e] = v.x; tile[4 * hl + 1][e] = v.y; tile[4 * hl + 2][e] = v.z; tile[4 * hl + 3][e] = v.w;
+        }
+        __syncthreads();
+        // write: one channel per warp iteration, 64 consecutive positions = 256 contiguous bytes
+        for (int ch = warp; ch < nc; ch += 8) {
+            float* o = out + (size_t)(cxyz + c0 + ch) * plane;
+            if (lane < ne) o[lane] = tile[ch][lane];
+            if (lane + 32 < ne) o[lane + 32] = tile[ch][lane + 32];
+        }
+        __syncthreads();
+    }
+}
+
 static inline dim3 chan_grid(int work, int c, int b) {
     // y = channel slabs: enough CTAs to fill the machine without one CTA per channel re-reading idx
     int y = c < 8 ? c : 8;
@@ -356,4 +409,19 @@ G4D_API int g4d_group_fused(int b, int n, int m, int c, int nsample, int use_xyz
     dim3 grid((unsigned)((plane4 + 255) / 256), (unsigned)slabs, (unsigned)b);
     group_fused_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, c, nsample, use_xyz, xyz, new_xyz, features, idx, out);
     return finish_launch("g4d group_fused");
+}
+
+// = g4d_group_fused with the features given POINT-major: feat_pm (b, n, c) fp32 (a transposed copy of the reference's (b, c, n)
+// tensor; the caller makes it once per feature tensor).  Same output, any nsample.
+G4D_API int g4d_group_fused_pm(int b, int n, int m, int c, int nsample, int use_xyz, const float* xyz, const float* new_xyz,
+                               const float* feat_pm, const int* idx, float* out, void* stream) {
+    if (b < 0 || n <= 0 || m < 0 || c <= 0 || nsample <= 0) return bad_arg("group_fused_pm: bad size");
+    if (b == 0 || m == 0) return 0;
+    if (!idx || !out || !feat_pm || (use_xyz && (!xyz || !new_xyz))) return bad_arg("group_fused_pm: null pointer");
+    if (b > 65535) return bad_arg("group_fused_pm: b > 65535");
+    if ((uintptr_t)feat_pm & 15) return bad_arg("group_fused_pm: feat_pm must be 16-byte aligned");
+    const long long plane = (long long)m * nsample;
+    dim3 grid((unsigned)((plane + GR_E - 1) / GR_E), (unsigned)b);
+    group_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, c, nsample, use_xyz, xyz, new_xyz, feat_pm, idx, out);
+    return finish_launch("g4d group_fused_pm");
 }

@@ -197,11 +197,11 @@ int fps_pruned_sorted(int b, int n, int m, const float4* sorted, long long strid
     if (n <= 1024) return launch_fps_pruned<128, 8>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
     if (n <= 2048) return launch_fps_pruned<128, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
     if (n <= 4096) return launch_fps_pruned<256, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
-    // Few clouds (at most one per SM, e.g. 120 per GPU when config c4 is sharded over 8 GPUs): 1024 threads x 8 points -- half
-    // the update path per step (emulation: 4.7 of 32 warps update, 150 instead of 280 instructions each); with more clouds than
-    // SMs two 512-thread CTAs per SM give the better throughput.  G4D_FPS_WIDE=0/1 overrides.
-    static const int wide_env = getenv("G4D_FPS_WIDE") ? atoi(getenv("G4D_FPS_WIDE")) : -1;
-    const bool wide = wide_env >= 0 ? wide_env != 0 : b <= sm_count();
+    // G4D_FPS_WIDE=1: 1024 threads x 8 points per cloud (half the update path per step, one CTA per SM).  Measured on B200 at
+    // 8192 -> 1024: 0.78 ms for <= 148 clouds against 0.79 ms for the 512 x 16 form, and 1.52 ms against 1.01 ms at 240 clouds
+    // (two waves instead of two clouds per SM): not worth a heuristic, off unless asked for.
+    static const int wide_env = getenv("G4D_FPS_WIDE") ? atoi(getenv("G4D_FPS_WIDE")) : 0;
+    const bool wide = wide_env != 0;
     if (wide) return launch_fps_pruned<1024, 8>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
     return launch_fps_pruned<512, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
 }

@@ -287,6 +287,7 @@ three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const 
     // fewer than 3 known points: the reference leaves distance 1e40 -> (float) inf and index 0 in the unused places
     const unsigned long long EMPTY = 0x7F80000000000000ull;
     unsigned long long k1 = EMPTY, k2 = EMPTY, k3 = EMPTY;
+    float d3 = INFINITY;                                             // distance part of k3
     // own-cell faces, for the per-row lower bounds
     const float fx0 = H.ox + (float)cx * H.h, fy0 = H.oy + (float)cy * H.h, fz0 = H.oz + (float)cz * H.h;
     const int maxring = max(max(max(cx, H.dx - 1 - cx), max(cy, H.dy - 1 - cy)), max(cz, H.dz - 1 - cz));
@@ -312,11 +313,15 @@ three_nn_grid_kernel(int n, int m, const float* __restrict__ unknown_all, const 
                     const int beg = __ldg(cell_start + row + xa), end = __ldg(cell_start + row + xb + 1);
                     for (int j = beg; j < end; ++j) {
                         const float4 p = __ldg(sorted + j);
-                        const unsigned long long key = nn_key(sqdist_ref(ux - p.x, uy - p.y, uz - p.z), __float_as_int(p.w));
-                        if (key < k3) {
-                            k3 = key;
-                            if (k3 < k2) { const unsigned long long tmp = k2; k2 = k3; k3 = tmp; }
-                            if (k2 < k1) { const unsigned long long tmp = k1; k1 = k2; k2 = tmp; }
+                        const float d = sqdist_ref(ux - p.x, uy - p.y, uz - p.z);
+                        if (d <= d3) {                               // one float compare rejects almost every candidate; NaN fails too
+                            const unsigned long long key = nn_key(d, __float_as_int(p.w));
+                            if (key < k3) {
+                                k3 = key;
+                                if (k3 < k2) { const unsigned long long tmp = k2; k2 = k3; k3 = tmp; }
+                                if (k2 < k1) { const unsigned long long tmp = k1; k1 = k2; k2 = tmp; }
+                                d3 = __uint_as_float((unsigned)(k3 >> 32));
+                            }
                         }
                     }
                 }

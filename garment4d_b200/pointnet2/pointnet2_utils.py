@@ -381,7 +381,21 @@ class _QueryAndGroupFused(Function):
         C = 0 if features is None else features.size(1)
         cout = (3 if use_xyz else 0) + C
         out = _f32(B, cout, P, nsample, device=xyz.device)
-        if nsample % 4 == 0:
+        if C >= 16 and B <= 65535:
+            # ball query, then the grouping pass from a POINT-major fp32 copy of the features (made once per feature tensor and
+            # remembered on it): 256-byte row gathers, shared-memory transpose, 256-byte runs per output channel
+            idx = BallQuery.apply(radius, nsample, xyz, new_xyz)
+            hit = getattr(features, "_g4d_pm32", None)
+            if hit is None or hit[1] != features._version:
+                hit = (features.detach().transpose(1, 2).contiguous(), features._version)
+                try:
+                    features._g4d_pm32 = hit
+                except Exception:
+                    pass
+            rc = _lib.lib().g4d_group_fused_pm(B, N, P, C, nsample, int(use_xyz), _lib.ptr(xyz), _lib.ptr(new_xyz),
+                                               _lib.ptr(hit[0]), _lib.ptr(idx), _lib.ptr(out), _lib.stream_ptr())
+            _lib.check(rc, "g4d_group_fused_pm")
+        elif nsample % 4 == 0:
             # ball query (uniform grid for large clouds), then ONE grouping pass (16-byte stores) for xyz, features and the cat
             idx = BallQuery.apply(radius, nsample, xyz, new_xyz)
             rc = _lib.lib().g4d_group_fused(B, N, P, C, nsample, int(use_xyz), _lib.ptr(xyz), _lib.ptr(new_xyz),

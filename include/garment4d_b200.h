@@ -95,6 +95,10 @@ int g4d_query_and_group(int b, int n, int m, int c, float radius, int nsample, i
  * group(features) and the concatenation in one write pass (pointnet2_utils.py:251-258).  out as g4d_query_and_group. */
 int g4d_group_fused(int b, int n, int m, int c, int nsample, int use_xyz, const float* xyz, const float* new_xyz,
                     const float* features, const int* idx, float* out, void* stream);
+/* = g4d_group_fused with the features POINT-major, feat_pm (b, n, c) fp32 (c > 0): contiguous 256-byte gathers and a
+ * shared-memory transpose to the channel-major output instead of one 4-byte gather per channel. */
+int g4d_group_fused_pm(int b, int n, int m, int c, int nsample, int use_xyz, const float* xyz, const float* new_xyz,
+                       const float* feat_pm, const int* idx, float* out, void* stream);
 
 /* Uniform-grid acceleration of the neighbour searches; results identical to the brute-force entry points above.
  * g4d_grid_build sorts each cloud's points by cell (cell edge >= min_cell, grown until <= 4096 cells; min_cell <= -1:
