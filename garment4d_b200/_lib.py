@@ -61,6 +61,8 @@ _SIGNATURES = {
     "g4d_sa_mlp_pack_params": (_i, [ctypes.POINTER(SaMlpDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_sa_mlp_max": (_i, [ctypes.POINTER(SaMlpDesc), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "g4d_debug_timeline": (None, [_vp]),
+    "g4d_debug_fps_phases": (_i, [_vp]),
+    "g4d_debug_mlp2_counters": (_i, [_vp]),
     "g4d_debug_fp_counters": (None, [_vp]),
     "g4d_fp_param_bytes": (_sz, [ctypes.POINTER(FpDesc)]),
     "g4d_fp_pack_params": (_i, [ctypes.POINTER(FpDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

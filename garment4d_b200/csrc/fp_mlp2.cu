@@ -1,4 +1,4 @@
-// Two-layer shared MLP over point-major rows on tcgen05, weights STREAMED from L2 (sm_100a).
+// Two-layer shared MLP over point-major rows on tcgen05, operands STREAMED by TMA (sm_100a).
 //
 // Replaces, for the coarser feature-propagation levels in eval mode (PointnetFPModule.forward, pointnet2_modules.py:138-156,
 // widths pointnet2encoder.py:91-96: FP1 352 -> 256 -> 128 on 1024 points per cloud, FP2 576 -> 512 -> 256 on 256 points):
@@ -8,21 +8,25 @@
 // concat).  Output: (b, c2, n) fp32 channel-major (the reference layout) and, optionally, (b, n, c2) fp16 point-major for the
 // next level's gather.
 //
-// The weights do not fit shared memory (FP2: 590 + 262 KB), so both GEMMs run a K-loop over 32-channel STAGES of a ring:
-//   stage = [A: 128 rows x 32 k fp16, canonical K-major, 8 KB | W: N rows x 32 k, canonical, N * 64 B]
-//   A producers (4 warps)  one thread per tile row: 4 x cp.async of 16 B per stage (layer 1 only; in layer 2 the A operand is
-//                          the hidden activation H, resident in shared memory)
-//   W loader (1 lane)      one cp.async.bulk (TMA bulk copy) per stage from the host-packed blob, completing on the stage's
-//                          full barrier (expect_tx)
-//   MMA issuer (1 warp)    warp-uniform code, elected lane: per stage 2 k-steps x (N / 256 rounded up) tcgen05.mma, then
-//                          tcgen05.commit -> the stage's empty barrier; D1 [128 x c1] and D2 [128 x c2] in TMEM (D2 reuses
-//                          D1's columns: c1 can take all 512)
-//   epilogue (8 warps)     two per TMEM lane quadrant, splitting the columns: D1 -> +b1, ReLU, fp16 -> H (canonical layout);
+// The weights do not fit shared memory (FP2: 590 + 262 KB), so both GEMMs run a K-loop over STAGES (32 or 16 channels) of a ring:
+//   stage = [A: 128 rows x ks k fp16, canonical K-major | W: N rows x ks k, canonical]
+//   loader (1 lane)        per stage ONE TMA tensor copy for A -- the activation matrix seen as a 3-D tensor
+//                          (8 channels, rows, c_in / 8) with box (8, 128, ks / 8), which lands as [k/8][row][k%8] = the UMMA
+//                          canonical no-swizzle K-major image; rows past the end are zero-filled by the hardware -- and one
+//                          cp.async.bulk for the host-packed W stage, both completing on the stage's full barrier (expect_tx).
+//                          In layer 2 the A operand is the hidden activation H, resident in shared memory: W only.
+//   MMA issuer (1 warp)    warp-uniform code, elected lane: per stage ks/16 k-steps x (N / 256 rounded up) tcgen05.mma, then
+//                          tcgen05.commit -> the stage's empty barrier; D1 [128 x c1] and D2 [128 x c2] in TMEM, in SEPARATE
+//                          columns when c1 + c2 <= 512 (then layer 1 of the next tile runs under epilogue 2 of this one)
+//   epilogue (8 warps)     two per TMEM lane quadrant, splitting the columns: D1 -> +b1, ReLU, fp16 -> H (canonical layout),
+//                          handed to the issuer in 64-channel pieces so layer 2 starts under the rest of epilogue 1;
 //                          D2 -> +b2, ReLU -> fp32 channel-major (lane = point: 128-byte coalesced stores per channel)
 //                          and fp16 point-major (64 contiguous bytes per thread and 32 channels)
-// One tile at a time per CTA (persistent, one CTA per SM): the tile's tensor work (FP2: 13 k cycles) dwarfs its hand-offs.
+// Persistent, one CTA per SM.
 #include <stdlib.h>
 #include <string.h>
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "common.cuh"
 #include "umma.cuh"
 #include "garment4d_b200.h"
@@ -30,46 +34,64 @@
 namespace g4d {
 
 constexpr int M2_TILE = 128;
-constexpr int M2_KS = 32;                               // channels per stage
-constexpr int M2_A_BYTES = M2_TILE * M2_KS * 2;        // 8 KB
-constexpr int M2_MAX_STAGES = 4;
+constexpr int M2_MAX_STAGES = 8;
+constexpr int M2_MAX_PIECES = 16;
 constexpr int M2_EPI_WARPS = 8;
-constexpr int M2_THREADS = (M2_EPI_WARPS + 1 + 4 + 1) * 32;      // epilogue | issuer | A producers | W loader = 448
+constexpr int M2_THREADS = (M2_EPI_WARPS + 1 + 1) * 32;          // epilogue | issuer | loader = 320
 
 struct Mlp2Layout {
-    int c_in, c1, c2, n1, n2, nst;                      // stages per tile in layer 1 / 2, ring depth
-    uint32_t w1_stage, w2_stage, stage_bytes;           // bytes of one W1 / W2 stage; ring slot size (A + max W)
+    int c_in, c1, c2, ks, n1, n2, nst;                  // channels per stage; stages per PASS in layer 1 / 2; ring depth
+    int npass, c1p;                                     // hidden channels are produced c1p (<= 256) at a time
+    int piece, npieces;                                 // H hand-over granularity (channels), pieces per pass
+    uint32_t a_bytes, w1_stage, w2_stage, stage_bytes;  // bytes of one A / W1 / W2 stage; ring slot size (A + max W)
     uint32_t off_w1, off_w2, off_b1, off_b2, blob_bytes;            // inside the blob (global memory)
-    uint32_t off_bias, off_h, off_ring, off_bar, total_smem, tmem_cols;
+    uint32_t off_bias, off_h, off_ring, off_bar, total_smem, tmem_cols, d2_col;
 };
+
+constexpr uint32_t M2_BAR_BYTES = 8u * (6 + 2 * M2_MAX_STAGES + M2_MAX_PIECES) + 16u;
 
 static bool mlp2_layout(const g4d_mlp2_desc* d, Mlp2Layout* L, const char** why) {
     if (d->c_in < 32 || d->c_in % 32 || d->c_in > 4096) { *why = "mlp2: c_in must be a multiple of 32 in [32, 4096]"; return false; }
-    if (d->c1 < 64 || d->c1 % 32 || d->c1 > 512) { *why = "mlp2: c1 must be a multiple of 32 in [64, 512]"; return false; }
+    if (d->c1 < 64 || d->c1 % 64 || d->c1 > 512 || (d->c1 > 256 && d->c1 % 128)) { *why = "mlp2: c1 must be a multiple of 64 in [64, 256] or of 128 up to 512"; return false; }
     if (d->c2 < 16 || d->c2 % 16 || d->c2 > 256) { *why = "mlp2: c2 must be a multiple of 16 in [16, 256]"; return false; }
     L->c_in = d->c_in; L->c1 = d->c1; L->c2 = d->c2;
-    L->n1 = d->c_in / M2_KS; L->n2 = d->c1 / M2_KS;
-    L->w1_stage = (uint32_t)d->c1 * M2_KS * 2; L->w2_stage = (uint32_t)d->c2 * M2_KS * 2;
+    // Hidden channels are produced in PASSES of at most 256: D1 [128 x c1p] and D2 [128 x c2] then always fit TMEM side by side,
+    // H is one pass wide (<= 64 KB), and layer 2 accumulates D2 over the passes (K = c1 split by pass).
+    L->npass = d->c1 > 256 ? 2 : 1;
+    L->c1p = d->c1 / L->npass;
+    L->off_bias = 0;                                    // b1 | b2 (fp32) at the start of shared memory
+    L->off_h = ((uint32_t)(d->c1 + d->c2) * 4 + 127) / 128 * 128;
+    L->off_ring = L->off_h + (uint32_t)M2_TILE * L->c1p * 2;
+    const uint32_t budget = 227u * 1024u - 1024u - 512u;
+    int ks = 32, nst = 0;
+    for (;; ks = 16) {                                  // 32 channels per stage unless that leaves fewer than 3 ring slots
+        const uint32_t wmax = (uint32_t)(L->c1p > d->c2 ? L->c1p : d->c2) * ks * 2;
+        L->a_bytes = (uint32_t)M2_TILE * ks * 2;
+        L->stage_bytes = L->a_bytes + wmax;
+        if (L->off_ring + 2u * L->stage_bytes + M2_BAR_BYTES > budget) {
+            if (ks == 16) { *why = "mlp2: shared memory footprint exceeds 227 KB"; return false; }
+            continue;
+        }
+        nst = (int)((budget - M2_BAR_BYTES - L->off_ring) / L->stage_bytes);
+        if (nst >= 3 || ks == 16) break;
+    }
+    if (nst > M2_MAX_STAGES) nst = M2_MAX_STAGES;
+    L->ks = ks; L->nst = nst;
+    L->n1 = d->c_in / ks; L->n2 = L->c1p / ks;          // stages per PASS
+    L->w1_stage = (uint32_t)L->c1p * ks * 2; L->w2_stage = (uint32_t)d->c2 * ks * 2;
     uint32_t o = 0;
-    L->off_w1 = o; o += L->w1_stage * (uint32_t)L->n1;
-    L->off_w2 = o; o += L->w2_stage * (uint32_t)L->n2;
+    L->off_w1 = o; o += L->w1_stage * (uint32_t)L->n1 * (uint32_t)L->npass;       // [pass][stage]
+    L->off_w2 = o; o += L->w2_stage * (uint32_t)L->n2 * (uint32_t)L->npass;       // [pass][stage]
     L->off_b1 = o; o += (uint32_t)d->c1 * 4;
     L->off_b2 = o; o += (uint32_t)d->c2 * 4;
     L->blob_bytes = o;
-    L->stage_bytes = M2_A_BYTES + (L->w1_stage > L->w2_stage ? L->w1_stage : L->w2_stage);
-    L->off_bias = 0;                                    // b1 | b2 (fp32) at the start of shared memory
-    L->off_h = ((uint32_t)(d->c1 + d->c2) * 4 + 127) / 128 * 128;
-    L->off_ring = L->off_h + (uint32_t)M2_TILE * d->c1 * 2;
-    const uint32_t budget = 227u * 1024u - 1024u - 512u;
-    const uint32_t bar_bytes = 8u * (4 + 2 * M2_MAX_STAGES) + 16u;
-    if (L->off_ring + 2u * L->stage_bytes + bar_bytes > budget) { *why = "mlp2: shared memory footprint exceeds 227 KB"; return false; }   // two stages at least
-    int nst = (int)((budget - bar_bytes - L->off_ring) / L->stage_bytes);
-    if (nst > M2_MAX_STAGES) nst = M2_MAX_STAGES;
-    L->nst = nst;
     L->off_bar = L->off_ring + (uint32_t)nst * L->stage_bytes;
-    L->total_smem = L->off_bar + bar_bytes;
+    L->total_smem = L->off_bar + M2_BAR_BYTES;
+    L->piece = (L->c1p % 128 == 0) ? 64 : L->c1p / 2;   // each half of the columns (one epilogue warp per quadrant) = whole pieces
+    L->npieces = L->c1p / L->piece;
+    L->d2_col = (uint32_t)L->c1p;
     uint32_t p2 = 32;
-    while (p2 < (uint32_t)d->c1 || p2 < (uint32_t)d->c2) p2 <<= 1;
+    while (p2 < (uint32_t)(L->c1p + d->c2)) p2 <<= 1;
     L->tmem_cols = p2;
     return true;
 }
@@ -78,11 +100,15 @@ struct Mlp2Args {
     Mlp2Layout L;
     long long rows;                  // b * n
     int n, ntiles;
-    const __half* x;                 // (rows, c_in) fp16 row-major
     const unsigned char* blob;       // packed weights (device)
     float* out_cm;                   // (b, c2, n) fp32
     __half* out_pm;                  // (b, n, c2) fp16 or null
+    int prof;                        // G4D_MLP2_PROF=1: CTA 0 accumulates role-level cycle counters (g4d_debug_mlp2_counters)
 };
+
+__device__ long long g_mlp2_prof[16];
+#define M2_T0() (pf ? clock64() : 0ll)
+#define M2_ACC(slot, t0) do { if (pf) acc[slot] += clock64() - (t0); } while (0)
 
 __device__ __forceinline__ void tmem_ld32_m2(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -98,25 +124,35 @@ __device__ __forceinline__ void tmem_ld32_m2(uint32_t taddr, uint32_t* r) {
     for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
 }
 
+// One box of the activation tensor map -> shared memory, completing (bytes) on an mbarrier.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 __global__ void __launch_bounds__(M2_THREADS, 1)
-fp_mlp2_kernel(const Mlp2Args a) {
+fp_mlp2_kernel(const Mlp2Args a, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Mlp2Layout& L = a.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* b1 = reinterpret_cast<const float*>(smem + L.off_bias);
     const float* b2 = b1 + L.c1;
-    // barriers: [0] biases, [1] tmem address, [2] d_full, [3] epi_done, then full[nst], empty[nst]
+    // barriers: [0] biases, [1] tmem address, [2] d1_full, [3] d2_full, [4] epi1 (unused slot kept for alignment), [5] epi2,
+    // then full[MAX_STAGES], empty[MAX_STAGES], h_ready[MAX_PIECES]
     const uint32_t bar0 = smem_u32(smem + L.off_bar);
-    const uint32_t bar_b = bar0, tmem_slot = bar0 + 8, bar_dfull = bar0 + 16, bar_epi = bar0 + 24;
-    const uint32_t bar_full = bar0 + 32, bar_empty = bar_full + 8 * M2_MAX_STAGES;
+    const uint32_t bar_b = bar0, tmem_slot = bar0 + 8, bar_d1 = bar0 + 16, bar_d2 = bar0 + 24, bar_epi2 = bar0 + 40;
+    const uint32_t bar_full = bar0 + 48, bar_empty = bar_full + 8 * M2_MAX_STAGES, bar_h = bar_empty + 8 * M2_MAX_STAGES;
     const uint32_t s_h = smem_u32(smem + L.off_h), s_ring = smem_u32(smem + L.off_ring);
-    const int NST = L.nst, n1 = L.n1, n2 = L.n2, per_tile = n1 + n2;
+    const int NST = L.nst, n1 = L.n1, n2 = L.n2, NP = L.npass, ks = L.ks;
+    const bool pf = a.prof && blockIdx.x == 0;
 
     if (tid == 0) {
         mbar_init(bar_b, 1);
-        mbar_init(bar_dfull, 1);
-        mbar_init(bar_epi, M2_EPI_WARPS);
-        for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 5);   /* 4 A-producer warps + the W loader */ mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_d1, 1);
+        mbar_init(bar_d2, 1);
+        mbar_init(bar_epi2, M2_EPI_WARPS);
+        for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int j = 0; j < L.npieces; ++j) mbar_init(bar_h + 8 * j, 4);     // the four quadrant warps of the half that owns the piece
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(tmem_slot, L.tmem_cols);
@@ -130,112 +166,86 @@ fp_mlp2_kernel(const Mlp2Args a) {
     }
     const int bx = (int)blockIdx.x, gx = (int)gridDim.x;
     const int nq = bx < a.ntiles ? (a.ntiles - bx + gx - 1) / gx : 0;          // tiles of this CTA: bx + q * gx
-    // stage number g = q * per_tile + (stage within the tile); ring slot g % NST, phase (g / NST) & 1.  One filler side (the
-    // producers and the loader, each in program order) and one drainer (the issuer) per slot: the single phase bit is safe.
+    // Stage sequence of a tile: for each pass, n1 layer-1 stages then n2 layer-2 stages; running stage number g, ring slot g % NST,
+    // phase (g / NST) & 1.  One filler (the loader) and one drainer (the issuer) per slot, both in program order: the single phase
+    // bit is safe.  d1_full and the H pieces complete once per pass (phase number u = q * NP + pass), d2_full and epi2 once per
+    // tile, and their waiters wait for every phase.
 
-    if (warp == M2_EPI_WARPS + 5) {
-        // =========================== W LOADER ================================================================
+    if (warp == M2_EPI_WARPS + 1) {
+        // =========================== LOADER ==================================================================
         if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&xmap)) : "memory");
             uint32_t g = 0;
-            for (int q = 0; q < nq; ++q)
-                for (int st = 0; st < per_tile; ++st, ++g) {
-                    const uint32_t slot = g % NST, ph = (g / NST) & 1;
-                    mbar_wait(bar_empty + 8 * slot, ph ^ 1);       // (suspending wait: a nanosleep poll costs >= 256 ns per miss, and with 2-4 stages nearly every wait misses)
-                    const bool l1 = st < n1;
-                    const uint32_t bytes = l1 ? L.w1_stage : L.w2_stage;
-                    const unsigned char* src = a.blob + (l1 ? L.off_w1 + (size_t)st * L.w1_stage : L.off_w2 + (size_t)(st - n1) * L.w2_stage);
-                    mbar_expect_tx(bar_full + 8 * slot, bytes);                  // counts as this thread's arrival
-                    bulk_g2s(s_ring + slot * L.stage_bytes + M2_A_BYTES, src, bytes, bar_full + 8 * slot);
-                }
-        }
-    } else if (warp >= M2_EPI_WARPS + 1) {
-        // =========================== A PRODUCERS: one thread per tile row ====================================
-        // Software pipeline: the copies of up to LAG + 1 stages are in flight; a stage is handed over (arrive on its full barrier)
-        // LAG stages after it was issued.  LAG <= NST - 1, so the empty slot a new stage waits for was handed over long before.
-        const int r = (warp - (M2_EPI_WARPS + 1)) * 32 + lane;
-        const int LAG = NST - 1 < 3 ? NST - 1 : 3;
-        const uint32_t total = (uint32_t)nq * (uint32_t)per_tile;
-        uint32_t g = 0;
-        for (int q = 0; q < nq; ++q) {
-            const long long R = (long long)(bx + q * gx) * M2_TILE + r;
-            const bool live = R < a.rows;
-            const char* srow = reinterpret_cast<const char*>(a.x + (size_t)(live ? R : 0) * L.c_in);
-            for (int st = 0; st < per_tile; ++st, ++g) {
-                const uint32_t slot = g % NST, ph = (g / NST) & 1;
-                mbar_wait(bar_empty + 8 * slot, ph ^ 1);       // (suspending wait: a nanosleep poll costs >= 256 ns per miss, and with 2-4 stages nearly every wait misses)
-                if (st < n1) {
-                    const uint32_t sdst = s_ring + slot * L.stage_bytes + (uint32_t)r * 16;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)                                  // 4 chunks of 8 channels: [(k/8)][row][8]
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + c * (M2_TILE * 16)),
-                                     "l"(srow + (size_t)st * (M2_KS * 2) + c * 16), "r"(live ? 16 : 0) : "memory");
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");              // (an empty group for layer-2 stages: A = H)
-                if (g >= (uint32_t)LAG) {
-                    switch (LAG) {
-                        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-                        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-                        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-                        default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+            long long acc[1] = {0};
+            const long long tl = M2_T0();
+            for (int q = 0; q < nq; ++q) {
+                const int row0 = (bx + q * gx) * M2_TILE;
+                for (int p = 0; p < NP; ++p)
+                    for (int st = 0; st < n1 + n2; ++st, ++g) {
+                        const uint32_t slot = g % NST, ph = (g / NST) & 1;
+                        { const long long t0 = M2_T0(); mbar_wait(bar_empty + 8 * slot, ph ^ 1); M2_ACC(0, t0); }
+                        const uint32_t dst = s_ring + slot * L.stage_bytes, full = bar_full + 8 * slot;
+                        if (st < n1) {
+                            mbar_expect_tx(full, L.a_bytes + L.w1_stage);            // counts as this thread's arrival
+                            tma_load_3d(dst, &xmap, 0, row0, st * (ks >> 3), full);
+                            bulk_g2s(dst + L.a_bytes, a.blob + L.off_w1 + (size_t)(p * n1 + st) * L.w1_stage, L.w1_stage, full);
+                        } else {
+                            mbar_expect_tx(full, L.w2_stage);
+                            bulk_g2s(dst + L.a_bytes, a.blob + L.off_w2 + (size_t)(p * n2 + st - n1) * L.w2_stage, L.w2_stage, full);
+                        }
                     }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full + 8 * ((g - LAG) % NST));
-                }
             }
+            if (pf) { g_mlp2_prof[8] = acc[0]; g_mlp2_prof[9] = clock64() - tl; }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        fence_proxy_async();
-        __syncwarp();
-        for (uint32_t t = total > (uint32_t)LAG ? total - LAG : 0; t < total; ++t)
-            if (lane == 0) mbar_arrive(bar_full + 8 * (t % NST));
     } else if (warp == M2_EPI_WARPS) {
         // =========================== MMA ISSUER (warp-uniform, elected lane) =================================
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
-        const uint32_t idesc1 = umma_idesc(M2_TILE, L.c1 > 256 ? 256 : L.c1), idesc1b = umma_idesc(M2_TILE, L.c1 > 256 ? L.c1 - 256 : 16);
-        const uint32_t idesc2 = umma_idesc(M2_TILE, L.c2);
-        uint32_t g = 0, nepi = 0;
+        const uint32_t idesc1 = umma_idesc(M2_TILE, L.c1p), idesc2 = umma_idesc(M2_TILE, L.c2);
+        const int ksteps = ks >> 4;
+        uint32_t g = 0, u = 0;
+        long long acc[5] = {0, 0, 0, 0, 0};
+        const long long ti = M2_T0();
         for (int q = 0; q < nq; ++q) {
-            // ---- layer 1: D1 = X . W1^T   (needs D drained by the previous tile's epilogue 2)
-            mbar_wait_spin(bar_epi, (nepi + 1) & 1); ++nepi;
-            tc_fence_after();
-            for (int st = 0; st < n1; ++st, ++g) {
-                const uint32_t slot = g % NST, ph = (g / NST) & 1;
-                mbar_wait(bar_full + 8 * slot, ph);
-                tc_fence_after();
-                if (elect_one_sync()) {
-                    const uint32_t sa = s_ring + slot * L.stage_bytes, sw = sa + M2_A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint64_t ad = desc64(desc_lo(sa + k * (2 * M2_TILE * 16), M2_TILE * 16));
-                        umma_f16(tmem_u, ad, desc64(desc_lo(sw + k * (2 * L.c1 * 16), L.c1 * 16)), idesc1, (st | k) > 0);
-                        if (L.c1 > 256)
-                            umma_f16(tmem_u + 256, ad, desc64(desc_lo(sw + k * (2 * L.c1 * 16) + 256 * 16, L.c1 * 16)), idesc1b, (st | k) > 0);
+            for (int p = 0; p < NP; ++p, ++u) {
+                // ---- layer 1 of this pass: D1 = X . W1p^T.  (D1 was drained by the previous pass's epilogue 1: every H piece
+                // was waited for below.)
+                for (int st = 0; st < n1; ++st, ++g) {
+                    const uint32_t slot = g % NST, ph = (g / NST) & 1;
+                    { const long long t0 = M2_T0(); mbar_wait(bar_full + 8 * slot, ph); M2_ACC(0, t0); }
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t sa = s_ring + slot * L.stage_bytes, sw = sa + L.a_bytes;
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_f16(tmem_u, desc64(desc_lo(sa + k * (2 * M2_TILE * 16), M2_TILE * 16)),
+                                     desc64(desc_lo(sw + k * (2 * L.c1p * 16), L.c1p * 16)), idesc1, (st | k) > 0);
+                        umma_commit(bar_empty + 8 * slot);
+                        if (st == n1 - 1) umma_commit(bar_d1);
                     }
-                    umma_commit(bar_empty + 8 * slot);
-                    if (st == n1 - 1) umma_commit(bar_dfull);
+                    __syncwarp();
                 }
-                __syncwarp();
-            }
-            // ---- layer 2: D2 = H . W2^T   (needs H written by epilogue 1)
-            mbar_wait_spin(bar_epi, (nepi + 1) & 1); ++nepi;
-            tc_fence_after();
-            for (int st = 0; st < n2; ++st, ++g) {
-                const uint32_t slot = g % NST, ph = (g / NST) & 1;
-                mbar_wait(bar_full + 8 * slot, ph);
-                tc_fence_after();
-                if (elect_one_sync()) {
-                    const uint32_t sw = s_ring + slot * L.stage_bytes + M2_A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        umma_f16(tmem_u, desc64(desc_lo(s_h + (uint32_t)(2 * st + k) * (2 * M2_TILE * 16), M2_TILE * 16)),
-                                 desc64(desc_lo(sw + k * (2 * L.c2 * 16), L.c2 * 16)), idesc2, (st | k) > 0);
-                    umma_commit(bar_empty + 8 * slot);
-                    if (st == n2 - 1) umma_commit(bar_dfull);
+                // ---- layer 2 of this pass: D2 (+)= Hp . W2p^T, started piece by piece as epilogue 1 hands H over.  The first
+                // pass overwrites D2: epilogue 2 of the previous tile must have drained it.
+                if (p == 0 && q > 0) { const long long t0 = M2_T0(); mbar_wait_spin(bar_epi2, (q - 1) & 1); tc_fence_after(); M2_ACC(3, t0); }
+                int have = 0;
+                for (int st = 0; st < n2; ++st, ++g) {
+                    const int pc = (st * ks) / L.piece;
+                    if (pc >= have) { const long long t0 = M2_T0(); mbar_wait_spin(bar_h + 8 * pc, u & 1); tc_fence_after(); have = pc + 1; M2_ACC(2, t0); }
+                    const uint32_t slot = g % NST, ph = (g / NST) & 1;
+                    { const long long t0 = M2_T0(); mbar_wait(bar_full + 8 * slot, ph); M2_ACC(1, t0); }
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t sw = s_ring + slot * L.stage_bytes + L.a_bytes;
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_f16(tmem_u + L.d2_col, desc64(desc_lo(s_h + (uint32_t)(ksteps * st + k) * (2 * M2_TILE * 16), M2_TILE * 16)),
+                                     desc64(desc_lo(sw + k * (2 * L.c2 * 16), L.c2 * 16)), idesc2, (p | st | k) > 0);
+                        umma_commit(bar_empty + 8 * slot);
+                        if (st == n2 - 1 && p == NP - 1) umma_commit(bar_d2);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
+        if (pf && lane == 0) { for (int i = 0; i < 4; ++i) g_mlp2_prof[i] = acc[i]; g_mlp2_prof[4] = clock64() - ti; g_mlp2_prof[5] = nq; }
     } else {
         // =========================== EPILOGUE: warps q and q+4 own TMEM lanes 32q..32q+31, half the columns each ====
         mbar_wait(bar_b, 0);
@@ -243,40 +253,45 @@ fp_mlp2_kernel(const Mlp2Args a) {
         const int row = quad * 32 + lane;
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16);
         uint4* hd = reinterpret_cast<uint4*>(smem + L.off_h);
-        uint32_t nd = 0;
+        long long acc[4] = {0, 0, 0, 0};
+        uint32_t u = 0;
         for (int q = 0; q < nq; ++q) {
             const long long R = (long long)(bx + q * gx) * M2_TILE + row;
             const bool live = R < a.rows;
-            // ---- epilogue 1: D1 -> +b1, ReLU, fp16 -> H
-            mbar_wait(bar_dfull, nd & 1); ++nd;
-            tc_fence_after();
-            {
-                const int c_lo = half * (L.c1 / 2), c_hi = c_lo + L.c1 / 2;      // c1 / 2 is a multiple of 16
+            // ---- epilogue 1, once per pass: D1 -> +b1, ReLU, fp16 -> H.  (d1_full of a pass is committed after the previous pass's
+            // layer-2 MMAs, so H is no longer being read.)
+            for (int p = 0; p < NP; ++p, ++u) {
+                { const long long t0 = M2_T0(); mbar_wait(bar_d1, u & 1); M2_ACC(0, t0); }
+                tc_fence_after();
+                const long long te1 = M2_T0();
+                const float* b1p = b1 + p * L.c1p;
+                const int c_lo = half * (L.c1p / 2), c_hi = c_lo + L.c1p / 2;    // c1p / 2 is a multiple of 32
 #pragma unroll 1
                 for (int c = c_lo; c < c_hi; c += 32) {
                     uint32_t v[32];
-                    tmem_ld32_m2(taddr + c, v);                               // (the last chunk of a 16-multiple half reads 16 columns too many: ignored)
-                    const int nu = (c_hi - c) >= 32 ? 4 : 2;
+                    tmem_ld32_m2(taddr + c, v);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (u < nu) {
-                            const float4 ba = *reinterpret_cast<const float4*>(b1 + c + 8 * u), bb = *reinterpret_cast<const float4*>(b1 + c + 8 * u + 4);
-                            hd[(size_t)((c >> 3) + u) * M2_TILE + row] =
-                                make_uint4(pack_relu_f16x2(__uint_as_float(v[8 * u]) + ba.x, __uint_as_float(v[8 * u + 1]) + ba.y),
-                                           pack_relu_f16x2(__uint_as_float(v[8 * u + 2]) + ba.z, __uint_as_float(v[8 * u + 3]) + ba.w),
-                                           pack_relu_f16x2(__uint_as_float(v[8 * u + 4]) + bb.x, __uint_as_float(v[8 * u + 5]) + bb.y),
-                                           pack_relu_f16x2(__uint_as_float(v[8 * u + 6]) + bb.z, __uint_as_float(v[8 * u + 7]) + bb.w));
-                        }
+                    for (int w = 0; w < 4; ++w) {
+                        const float4 ba = *reinterpret_cast<const float4*>(b1p + c + 8 * w), bb = *reinterpret_cast<const float4*>(b1p + c + 8 * w + 4);
+                        hd[(size_t)((c >> 3) + w) * M2_TILE + row] =
+                            make_uint4(pack_relu_f16x2(__uint_as_float(v[8 * w]) + ba.x, __uint_as_float(v[8 * w + 1]) + ba.y),
+                                       pack_relu_f16x2(__uint_as_float(v[8 * w + 2]) + ba.z, __uint_as_float(v[8 * w + 3]) + ba.w),
+                                       pack_relu_f16x2(__uint_as_float(v[8 * w + 4]) + bb.x, __uint_as_float(v[8 * w + 5]) + bb.y),
+                                       pack_relu_f16x2(__uint_as_float(v[8 * w + 6]) + bb.z, __uint_as_float(v[8 * w + 7]) + bb.w));
+                    }
+                    if ((c + 32) % L.piece == 0) {                                // a piece of H is complete in this warp
+                        tc_fence_before();
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_h + 8 * (c / L.piece));
                     }
                 }
+                M2_ACC(1, te1);
             }
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_epi);
             // ---- epilogue 2: D2 -> +b2, ReLU -> fp32 channel-major + fp16 point-major
-            mbar_wait(bar_dfull, nd & 1); ++nd;
+            { const long long t0 = M2_T0(); mbar_wait(bar_d2, q & 1); M2_ACC(2, t0); }
             tc_fence_after();
+            const long long te2 = M2_T0();
             {
                 const unsigned cloud = live ? (unsigned)((unsigned long long)R / (unsigned)a.n) : 0u;
                 const int pt = live ? (int)(R - (long long)cloud * a.n) : 0;
@@ -286,7 +301,7 @@ fp_mlp2_kernel(const Mlp2Args a) {
 #pragma unroll 1
                 for (int c = c_lo; c < c_hi; c += 32) {
                     uint32_t v[32];
-                    tmem_ld32_m2(taddr + c, v);
+                    tmem_ld32_m2(taddr + L.d2_col + c, v);                    // (the last chunk of a short half reads columns past it: ignored)
                     const int nv = (c_hi - c) >= 32 ? 32 : (c_hi - c);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -307,8 +322,10 @@ fp_mlp2_kernel(const Mlp2Args a) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_epi);
+            if (lane == 0) mbar_arrive(bar_epi2);
+            M2_ACC(3, te2);
         }
+        if (pf && tid == 0) for (int i = 0; i < 4; ++i) g_mlp2_prof[10 + i] = acc[i];
     }
 
     tc_fence_before();
@@ -316,9 +333,34 @@ fp_mlp2_kernel(const Mlp2Args a) {
     if (warp == 0) tmem_dealloc(tmem, L.tmem_cols);
 }
 
+// The activation rows as a TMA tensor: (8 channels, rows, c_in / 8) fp16 with strides (2, c_in * 2, 16) bytes, box (8, 128, ks / 8).
+static int make_x_map(CUtensorMap* map, const void* x, long long rows, int c_in, int ks) {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+        if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) { set_error("mlp2_rows: cuTensorMapEncodeTiled not available from the driver"); return 1; }
+        encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    }
+    const cuuint64_t dims[3] = {8, (cuuint64_t)rows, (cuuint64_t)(c_in / 8)};
+    const cuuint64_t strides[2] = {(cuuint64_t)c_in * 2, 16};
+    const cuuint32_t box[3] = {8, (cuuint32_t)M2_TILE, (cuuint32_t)(ks / 8)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("mlp2_rows: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return 1; }
+    return 0;
+}
+
 }  // namespace g4d
 
 using namespace g4d;
+
+// Measurement aid: role-level cycle counters of CTA 0 of the last g4d_mlp2_rows launch made with G4D_MLP2_PROF=1 (16 int64):
+// issuer [0] wait full (layer 1) [1] wait full (layer 2) [2] wait H [3] wait epilogue 2 [4] loop [5] tiles; loader [8] wait empty [9] loop;
+// epilogue warp 0 [10] wait D1 [11] epilogue 1 [12] wait D2 [13] epilogue 2.
+G4D_API int g4d_debug_mlp2_counters(long long* out16) { return (int)cudaMemcpyFromSymbol(out16, g_mlp2_prof, sizeof(long long) * 16); }
 
 G4D_API size_t g4d_mlp2_param_bytes(const g4d_mlp2_desc* d) {
     Mlp2Layout L; const char* why = nullptr;
@@ -326,7 +368,7 @@ G4D_API size_t g4d_mlp2_param_bytes(const g4d_mlp2_desc* d) {
     return L.blob_bytes;
 }
 
-// w1 (c1, c_in), w2 (c2, c1) fp32 folded weights, b1 (c1), b2 (c2) -> blob (host memory): per 32-channel stage the UMMA
+// w1 (c1, c_in), w2 (c2, c1) fp32 folded weights, b1 (c1), b2 (c2) -> blob (host memory): per stage (32 or 16 channels) the UMMA
 // canonical K-major image of that K range ([k/8][row][k%8] fp16), then the fp32 biases.  Fails ("fp16 range") when a weight does
 // not fit fp16.
 G4D_API int g4d_mlp2_pack_params(const g4d_mlp2_desc* d, const float* w1, const float* b1, const float* w2, const float* b2, void* blob) {
@@ -336,19 +378,22 @@ G4D_API int g4d_mlp2_pack_params(const g4d_mlp2_desc* d, const float* w1, const 
     unsigned char* out = (unsigned char*)blob;
     memset(out, 0, L.blob_bytes);
     bool ok = true;
-    auto put = [&](__half* base, int R, int r, int kl, float v) {       // kl: k within the stage (0..31)
+    const int KS = L.ks;
+    auto put = [&](__half* base, int R, int r, int kl, float v) {       // kl: k within the stage
         base[((size_t)(kl / 8) * R + r) * 8 + (kl % 8)] = __float2half_rn(v);
         ok &= fabsf(v) <= 65504.f;
     };
-    for (int st = 0; st < L.n1; ++st) {
-        __half* W = (__half*)(out + L.off_w1 + (size_t)st * L.w1_stage);
-        for (int o = 0; o < L.c1; ++o)
-            for (int kl = 0; kl < M2_KS; ++kl) put(W, L.c1, o, kl, w1[(size_t)o * L.c_in + st * M2_KS + kl]);
-    }
-    for (int st = 0; st < L.n2; ++st) {
-        __half* W = (__half*)(out + L.off_w2 + (size_t)st * L.w2_stage);
-        for (int o = 0; o < L.c2; ++o)
-            for (int kl = 0; kl < M2_KS; ++kl) put(W, L.c2, o, kl, w2[(size_t)o * L.c1 + st * M2_KS + kl]);
+    for (int p = 0; p < L.npass; ++p) {
+        for (int st = 0; st < L.n1; ++st) {
+            __half* W = (__half*)(out + L.off_w1 + (size_t)(p * L.n1 + st) * L.w1_stage);
+            for (int o = 0; o < L.c1p; ++o)
+                for (int kl = 0; kl < KS; ++kl) put(W, L.c1p, o, kl, w1[(size_t)(p * L.c1p + o) * L.c_in + st * KS + kl]);
+        }
+        for (int st = 0; st < L.n2; ++st) {
+            __half* W = (__half*)(out + L.off_w2 + (size_t)(p * L.n2 + st) * L.w2_stage);
+            for (int o = 0; o < L.c2; ++o)
+                for (int kl = 0; kl < KS; ++kl) put(W, L.c2, o, kl, w2[(size_t)o * L.c1 + p * L.c1p + st * KS + kl]);
+        }
     }
     memcpy(out + L.off_b1, b1, sizeof(float) * L.c1);
     memcpy(out + L.off_b2, b2, sizeof(float) * L.c2);
@@ -370,12 +415,16 @@ G4D_API int g4d_mlp2_rows(const g4d_mlp2_desc* d, const void* params_dev, int b,
     if (a.rows > 0x7FFFFF00ll) return bad_arg("mlp2_rows: b*n must stay below 2^31");
     a.n = n;
     a.ntiles = (int)((a.rows + M2_TILE - 1) / M2_TILE);
-    a.x = (const __half*)x_h; a.blob = (const unsigned char*)params_dev;
+    a.blob = (const unsigned char*)params_dev;
+    static const int prof_env = getenv("G4D_MLP2_PROF") ? atoi(getenv("G4D_MLP2_PROF")) : 0;
+    a.prof = prof_env;
+    CUtensorMap xmap;
+    if (make_x_map(&xmap, x_h, a.rows, a.L.c_in, a.L.ks)) return 1;
     a.out_cm = out_cm; a.out_pm = (__half*)out_pm;
     cudaError_t e = cudaFuncSetAttribute(fp_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
     if (e != cudaSuccess) { set_error("mlp2_rows: shared memory opt-in (%u B): %s", a.L.total_smem, cudaGetErrorString(e)); return (int)e; }
     int grid = sm_count();
     if (grid > a.ntiles) grid = a.ntiles;
-    fp_mlp2_kernel<<<grid, M2_THREADS, a.L.total_smem, (cudaStream_t)stream>>>(a);
+    fp_mlp2_kernel<<<grid, M2_THREADS, a.L.total_smem, (cudaStream_t)stream>>>(a, xmap);
     return finish_launch("g4d mlp2_rows");
 }

@@ -22,8 +22,12 @@
 
 namespace g4d {
 
-template <int T, int PPT>
-__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
+// PROF: clock() phase sums of every warp of cloud 0 (tools/fps_phases.py); a measurement build, never launched by the product path.
+__device__ unsigned g_fps_prof[32 * 20];
+__device__ __forceinline__ unsigned clk() { unsigned c; asm volatile("mov.u32 %0, %%clock;" : "=r"(c)); return c; }
+
+template <int T, int PPT, bool PROF = false>
+__global__ void __launch_bounds__(T, (T <= 512 && !PROF) ? 2 : 1)
 fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all, long long cloud_stride, int* __restrict__ idx_all,
                   float* __restrict__ new_xyz_all) {
     extern __shared__ __align__(16) float soa[];           // xs[PPT][T], ys[PPT][T], zs[PPT][T]
@@ -90,11 +94,15 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
     unsigned out_k = 0;
     float out_x = 0.f, out_y = 0.f, out_z = 0.f;
 
+    unsigned pf[2][8] = {}, pn[2] = {0, 0}, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
     for (int j = 1; j < m; ++j) {
+        if (PROF) c0 = clk();
         const float dcx = ccx - x1, dcy = ccy - y1, dcz = ccz - z1;
         const float d2c = dcx * dcx + dcy * dcy + dcz * dcz;
         const bool need = d2c < thr;
-        if (__any_sync(0xFFFFFFFFu, need) || j == 1) {
+        const bool wneed = __any_sync(0xFFFFFFFFu, need) || j == 1;
+        if (PROF) c1 = c2 = c3 = clk();
+        if (wneed) {
             if (need) {
 #pragma unroll
                 for (int i = 0; i < PPT; ++i) {
@@ -133,6 +141,7 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
                 vb = __float_as_int(tmax);
                 stale_thr = true;
             }
+            if (PROF) { __syncwarp(); c2 = clk(); }
             // warp candidate: max value; the tie-break reduction only runs when several lanes share the maximum
             wv = __reduce_max_sync(0xFFFFFFFFu, vb);
             const unsigned m1 = __ballot_sync(0xFFFFFFFFu, vb == wv);
@@ -141,13 +150,16 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
                 const unsigned wk = __reduce_min_sync(0xFFFFFFFFu, vb == wv ? tkey : 0xFFFFFFFFu);
                 holder = (vb == wv) && (tkey == wk);
             }
+            if (PROF) c3 = clk();
         }
         const int par = j & 1;
         if (holder) {                                      // cached between updates of this warp
             slot_v[par][warp] = vb; slot_k[par][warp] = tkey;
             slot_p[par][warp][0] = bx; slot_p[par][warp][1] = by; slot_p[par][warp][2] = bz;
         }
+        if (PROF) c4 = clk();
         __syncthreads();
+        if (PROF) c5 = clk();
         const int sv = lane < NW ? slot_v[par][lane] : INT_MIN;
         const int bv = __reduce_max_sync(0xFFFFFFFFu, sv);
         unsigned m2 = __ballot_sync(0xFFFFFFFFu, sv == bv);
@@ -158,6 +170,7 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
         }
         const int wl = __ffs(m2) - 1;
         x1 = slot_p[par][wl][0]; y1 = slot_p[par][wl][1]; z1 = slot_p[par][wl][2];
+        if (PROF) { c6 = clk() + (__float_as_uint(x1) & 0u); }
         // Results are latched in the lanes of warp 0 and written out 32 steps at a time: a global store in every step
         // would make each barrier wait for its acknowledgement (BAR.SYNC drains the warp's outstanding stores).
         if (warp == 0) {
@@ -175,12 +188,26 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
             thr = s * s * 1.0002f;
             stale_thr = false;
         }
+        if (PROF && j > 1) {
+            const unsigned dd[7] = {c1 - c0, c2 - c1, c3 - c2, c4 - c3, c5 - c4, c6 - c5, clk() - c6};
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { pf[0][i] += wneed ? 0u : dd[i]; pf[1][i] += wneed ? dd[i] : 0u; }
+            pn[0] += wneed ? 0u : 1u; pn[1] += wneed ? 1u : 0u;
+        }
+    }
+    if (PROF && blockIdx.x == 0 && lane == 0) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) g_fps_prof[warp * 20 + f * 8 + i] = pf[f][i];
+            g_fps_prof[warp * 20 + 16 + f] = pn[f];
+        }
     }
 }
 
-template <int T, int PPT>
+template <int T, int PPT, bool PROF = false>
 static int launch_fps_pruned(int b, int n, int m, int lg, const float4* sorted, long long stride, int* idx, float* new_xyz, cudaStream_t s) {
-    auto kern = fps_pruned_kernel<T, PPT>;
+    auto kern = fps_pruned_kernel<T, PPT, PROF>;
     size_t smem = (size_t)T * PPT * (3 * sizeof(float) + sizeof(unsigned short));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("fps_pruned: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e)); return (int)e; }
@@ -203,12 +230,19 @@ int fps_pruned_sorted(int b, int n, int m, const float4* sorted, long long strid
     static const int wide_env = getenv("G4D_FPS_WIDE") ? atoi(getenv("G4D_FPS_WIDE")) : 0;
     const bool wide = wide_env != 0;
     if (wide) return launch_fps_pruned<1024, 8>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
+    static const bool prof = getenv("G4D_FPS_PROF") != nullptr;
+    if (prof) return launch_fps_pruned<512, 16, true>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
     return launch_fps_pruned<512, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
 }
 
 }  // namespace g4d
 
 using namespace g4d;
+
+// Measurement aid: phase sums written by the last G4D_FPS_PROF=1 launch (32 warps x 20 words), see tools/fps_phases.py.
+G4D_API int g4d_debug_fps_phases(unsigned* out640) {
+    return (int)cudaMemcpyFromSymbol(out640, g_fps_prof, sizeof(unsigned) * 640);
+}
 
 // = g4d_fps_gather (same idx and new_xyz) given a grid built over xyz by g4d_grid_build (any cell size): the
 // cell-sorted order gives every thread a compact clump of points, which makes the exact pruning effective.

@@ -153,6 +153,10 @@ int g4d_sa_mlp_max(const g4d_sa_mlp_desc* d, const void* params_dev, int b, int 
 /* debug aid: clock64() timeline of slot 0 of CTA 0 of the following g4d_sa_mlp_max launches (buf: >= 256 int64 on the device;
  * NULL = off) */
 void g4d_debug_timeline(void* buf);
+/* debug aid: clock() phase sums (32 warps x 20 words) of cloud 0 of the last pruned-FPS launch made with G4D_FPS_PROF=1 */
+int g4d_debug_fps_phases(unsigned* out640);
+/* debug aid: role-level cycle counters (16 int64) of CTA 0 of the last g4d_mlp2_rows launch made with G4D_MLP2_PROF=1 */
+int g4d_debug_mlp2_counters(long long* out16);
 
 /* Fused feature propagation (no skip features) + optional segmentation head on tcgen05: inverse-distance weights
  * from three_nn's squared distances, 3-tap interpolation, the FP module's 2-layer 1x1-conv MLP (eval BN folded, ReLU)
