@@ -84,6 +84,10 @@ _SIGNATURES = {
     "g4d_scatter_det_build": (_i, [_i, _i, _i, _vp, _vp, _vp]),
     "g4d_scatter_det_apply": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4d_select_points": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_knn_points": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_knn_inverse_weights": (_i, [ctypes.c_longlong, _i, _i, _vp, _vp, _vp]),
+    "g4d_knn_blend_weights": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_smooth_weights": (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_pe_mlp_max": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_batch_rodrigues": (_i, [_i, _vp, _vp, _vp]),
     "g4d_blend_shapes": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),

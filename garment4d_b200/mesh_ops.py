@@ -8,7 +8,13 @@ function signatures (modules/mesh_encoder.py).
   GarmentEncoderStack         the second set-abstraction stack on the selected garment points (mesh_encoder.py:54-78, 149-161):
                               two PointnetSAModuleMSG levels + the GroupAll summary module -- the fused tcgen05 route of
                               garment4d_b200.pointnet2 in eval mode.
+  knn_points                  chamferdist.knn_points as the model calls it (mesh_encoder.py:321-324, 541): g4d_knn_points.
+  smoothing_operator          normalize(adj_old) - I of mesh_encoder.py:386 as a CSR triple on the device (built once per mesh).
+  lbs_garment_interpolation   MeshEncoder.lbs_garment_interpolation (mesh_encoder.py:312-410): one K-NN search instead of three,
+                              the weighted gather of the skinning weights without the (F, body_v, K, 24) intermediate, the 100
+                              smoothing steps and both skinning passes (g4d_lbs_skin) -- no torch math on the data path.
 """
+from collections import namedtuple
 import torch
 import torch.nn as nn
 
@@ -148,3 +154,126 @@ class PositionalEncoding(nn.Module):
         if not ok:
             return _pe_reference_composition(self.group, self.mlp, xyz, new_xyz, features)
         return _PositionalEncodingFn.apply(self.group, self.mlp, xyz, new_xyz, features, l1.weight, l1.bias, l2.weight, l2.bias)
+
+
+# ---- lbs_garment_interpolation (mesh_encoder.py:312-410) ------------------------------------------------------------------------
+KNN = namedtuple("KNN", ["dists", "idx"])      # the fields of chamferdist's / pytorch3d's knn_points result the model reads
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def knn_points(p1, p2, K=1):
+    """chamferdist.knn_points(p1, p2, K) as called at mesh_encoder.py:321-324: p1 (B,N,3), p2 (B,P,3) ->
+    KNN(dists (B,N,K) squared distances ascending, idx (B,N,K) int64).  Equal distances come in ascending index order.
+    K <= min(256, P), P <= 8192."""
+    if not (p1.is_cuda and p2.is_cuda):
+        raise _lib.G4DError("knn_points: CUDA tensors required (there is no CPU path)")
+    a, b = _f32c(p1), _f32c(p2)
+    B, N, _ = a.shape
+    P = b.shape[1]
+    d = torch.empty(B, N, K, dtype=torch.float32, device=a.device)
+    i = torch.empty(B, N, K, dtype=torch.int32, device=a.device)
+    _lib.check(_lib.lib().g4d_knn_points(B, N, P, K, _lib.ptr(a), _lib.ptr(b), _lib.ptr(d), _lib.ptr(i), _lib.stream_ptr()), "g4d_knn_points")
+    return KNN(d, i.long())
+
+
+def smoothing_operator(adj, device):
+    """normalize(adj_old) - I (mesh_encoder.py:386; pygcn/utils.py:56-63 row normalisation) as (rowptr, col, val) int32/int32/fp32
+    device tensors.  adj: the symmetric 0/1 garment-mesh adjacency as a dense (G,G) tensor, a torch sparse tensor, or anything
+    with .tocoo() (scipy)."""
+    if hasattr(adj, "tocoo"):
+        coo = adj.tocoo()
+        row, col = torch.as_tensor(coo.row, dtype=torch.int64), torch.as_tensor(coo.col, dtype=torch.int64)
+        val, G = torch.as_tensor(coo.data, dtype=torch.float32), int(coo.shape[0])
+    elif adj.layout == torch.strided:
+        A = adj.detach().cpu().to(torch.float32)
+        row, col = torch.nonzero(A, as_tuple=True)
+        val, G = A[row, col], int(A.shape[0])
+    else:
+        A = adj.detach().cpu().coalesce()
+        (row, col), val, G = A.indices(), A.values().to(torch.float32), int(A.shape[0])
+    rowsum = torch.zeros(G, dtype=torch.float32).index_add_(0, row, val)
+    r_inv = torch.where(rowsum != 0, 1.0 / rowsum, torch.zeros_like(rowsum))      # r_inv[isinf] = 0
+    diag = torch.arange(G, dtype=torch.int64)
+    key = torch.cat([row, diag]) * G + torch.cat([col, diag])                      # entries of r_inv * A - I, duplicates summed
+    v = torch.cat([val * r_inv[row], -torch.ones(G)])
+    ukey, inv = torch.unique(key, sorted=True, return_inverse=True)
+    uval = torch.zeros(ukey.numel(), dtype=torch.float32).index_add_(0, inv, v)
+    urow, ucol = ukey // G, ukey % G
+    rowptr = torch.zeros(G + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(urow, minlength=G), 0)
+    return rowptr.to(torch.int32).to(device), ucol.to(torch.int32).to(device), uval.to(device)
+
+
+def lbs_garment_interpolation(pred_template_garment_v, Tpose_vertices, Tpose_root_joints, zeropose_vertices, body_model, gt_pose,
+                              T_J_regressor, T_lbs_weights, K=3, smooth=None, smooth_iters=100, coeff=0.1):
+    """MeshEncoder.lbs_garment_interpolation (mesh_encoder.py:312-410), same arguments and results:
+        pred_template_garment_v (B,G,3), Tpose_vertices (B,P,3) (or (B,1,P,3)), Tpose_root_joints (B,3), zeropose_vertices (B,T,P,3),
+        body_model: anything with .parents, gt_pose (B,T,72), T_J_regressor (B,T,J,P), T_lbs_weights (B,T,P,J)
+        -> lbs_pred_garment_v (B,T,G,3), nn (KNN with K = 1), stage-1 (inverse-posed) garment (B,T,G,3)
+    smooth: the (rowptr, col, val) triple of smoothing_operator() -- the reference rebuilds normalize(self.adj_old) - I on the host
+    on every call (:386-387); required when K > 1."""
+    from . import lbs as L
+    dev = pred_template_garment_v.device
+    if dev.type != "cuda":
+        raise _lib.G4DError("lbs_garment_interpolation: CUDA tensors required (there is no CPU path)")
+    assert pred_template_garment_v.dim() == 3 and pred_template_garment_v.shape[2] == 3
+    assert gt_pose.dim() == 3 and gt_pose.shape[2] == 72
+    lib = _lib.lib()
+    st = _lib.stream_ptr()
+    B, G, _ = pred_template_garment_v.shape
+    T = gt_pose.shape[1]
+    J = T_J_regressor.shape[2]
+    parents = body_model.parents if hasattr(body_model, "parents") else body_model
+    gt_pose_mat = L.batch_rodrigues(_f32c(gt_pose).reshape(-1, 3)).reshape(B * T, 24, 3, 3)                  # :318
+    q = (_f32c(pred_template_garment_v) + _f32c(Tpose_root_joints).reshape(B, 1, 3)).contiguous()            # :320
+    body = _f32c(Tpose_vertices).reshape(B, -1, 3)
+    P = body.shape[1]
+    # :321-324 -- one search: the K = min(64, K) and K = 1 results are prefixes of the K one
+    dK = torch.empty(B, G, K, dtype=torch.float32, device=dev)
+    iK = torch.empty(B, G, K, dtype=torch.int32, device=dev)
+    _lib.check(lib.g4d_knn_points(B, G, P, K, _lib.ptr(q), _lib.ptr(body), _lib.ptr(dK), _lib.ptr(iK), st), "g4d_knn_points")
+    K64 = min(64, K)
+    nn = KNN(dK[:, :, :1].contiguous(), iK[:, :, :1].long())
+    # :326-335 -- the fixed inverse template pose
+    inv_pose = torch.zeros(B, 24, 3, dtype=torch.float32, device=dev)
+    inv_pose[:, 0, 0] = -3.141592653589793 / 2
+    inv_pose[:, 1, 1] = 0.15
+    inv_pose[:, 2, 1] = -0.15
+    inv_mat = L.batch_rodrigues(inv_pose.reshape(-1, 3)).reshape(B, 24, 3, 3)
+    Jreg = _f32c(T_J_regressor)
+    inv_J = L.vertices2jointsB(Jreg[:, 0].contiguous(), body)
+    _, inv_A = L.batch_rigid_transform(inv_mat, inv_J, parents)
+    # :339-347 -- skinning weights of the garment in the T pose: inverse-distance blend of the K64 nearest body vertices
+    Wall = _f32c(T_lbs_weights)                                                                               # (B,T,P,J)
+    w64 = torch.empty(B, G, K64, dtype=torch.float32, device=dev)
+    _lib.check(lib.g4d_knn_inverse_weights(B * G, K, K64, _lib.ptr(dK), _lib.ptr(w64), st), "g4d_knn_inverse_weights")
+    W0 = Wall[:, 0].contiguous()
+    inv_nn_W = torch.empty(B, G, J, dtype=torch.float32, device=dev)
+    _lib.check(lib.g4d_knn_blend_weights(B, 1, G, P, J, K64, K, _lib.ptr(iK), _lib.ptr(w64), _lib.ptr(W0), _lib.ptr(inv_nn_W), st),
+               "g4d_knn_blend_weights")
+    stage1_b = L.skin(q, inv_A, inv_nn_W)                                                                     # :357-362  (B,G,3)
+    stage1 = stage1_b.reshape(B, 1, G, 3).repeat(1, T, 1, 1).reshape(B * T, G, 3).contiguous()
+    # :364-369 -- the posed skeleton of every frame
+    Jz = L.vertices2jointsB(Jreg.reshape(B * T, J, -1), _f32c(zeropose_vertices).reshape(B * T, -1, 3))
+    _, A = L.batch_rigid_transform(gt_pose_mat, Jz, parents)
+    # :371-379 -- per-frame skinning weights of the garment
+    wK = torch.empty(B, G, K, dtype=torch.float32, device=dev)
+    _lib.check(lib.g4d_knn_inverse_weights(B * G, K, K, _lib.ptr(dK), _lib.ptr(wK), st), "g4d_knn_inverse_weights")
+    nn_W = torch.empty(B * T, G, J, dtype=torch.float32, device=dev)
+    Wf = Wall.reshape(B * T, P, J)
+    _lib.check(lib.g4d_knn_blend_weights(B, T, G, P, J, K, K, _lib.ptr(iK), _lib.ptr(wK), _lib.ptr(Wf), _lib.ptr(nn_W), st),
+               "g4d_knn_blend_weights")
+    if K > 1:                                                                                                 # :382-389
+        if smooth is None:
+            raise _lib.G4DError("lbs_garment_interpolation: K > 1 needs smooth = smoothing_operator(adj_old, device)")
+        rowptr, col, val = smooth
+        if rowptr.numel() != G + 1:
+            raise _lib.G4DError("lbs_garment_interpolation: the smoothing operator does not match the garment's vertex count")
+        tmp = torch.empty_like(nn_W)
+        _lib.check(lib.g4d_smooth_weights(B * T, G, J, int(smooth_iters), float(coeff), _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val),
+                                          _lib.ptr(nn_W), _lib.ptr(tmp), st), "g4d_smooth_weights")
+    out = L.skin(stage1, A, nn_W)                                                                             # :391-408
+    return out.reshape(B, T, G, 3), nn, stage1.reshape(B, T, G, 3)

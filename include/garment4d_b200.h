@@ -265,6 +265,22 @@ int g4d_pe_mlp_max(int b, int n, int p, int c, int nsample, const float* xyz, co
                    const int* idx, const float* w1t, const float* b1, const float* w2t, const float* b2, float* out,
                    signed char* argmax, void* stream);
 
+/* ---- garment skinning by interpolated body weights: MeshEncoder.lbs_garment_interpolation (modules/mesh_encoder.py:312-410) ---- */
+/* K nearest reference points of every query, ascending squared distance, equal distances by ascending index: replaces
+ * chamferdist.knn_points as called at mesh_encoder.py:321-324 (its K = 64 and K = 1 results are prefixes of the K = LBSK one).
+ * query (b,nq,3), ref (b,nr,3) -> dist2 (b,nq,K), idx (b,nq,K) int32.  1 <= K <= min(256, nr), nr <= 8192. */
+int g4d_knn_points(int b, int nq, int nr, int K, const float* query, const float* ref, float* dist2, int* idx, void* stream);
+/* mesh_encoder.py:341-345 / :371-375: w (rows,k) = 1 / dist2[:, :k] with inf -> 0, divided by the row sum, inf -> 0; dist2 (rows,ld) */
+int g4d_knn_inverse_weights(long long rows, int ld, int k, const float* dist2, float* w, void* stream);
+/* mesh_encoder.py:339-346 / :377-379 without the (F, body_v, K, J) intermediate: out (B*T,nq,J) = sum_k w (B,nq,K)[..,k] *
+ * W (B*T,P,J)[f, idx (B,nq,ld_idx)[..,k], :] with f = b*T + t.  J <= 32. */
+int g4d_knn_blend_weights(int B, int T, int nq, int P, int J, int K, int ld_idx, const int* idx, const float* w, const float* W,
+                          float* out, void* stream);
+/* mesh_encoder.py:382-389: `iters` steps of x <- x + coeff * Adj . x per frame; x (F,G,J) in/out, tmp (F,G,J) scratch,
+ * Adj (G x G) in CSR (rowptr G+1, col, val). */
+int g4d_smooth_weights(int F, int G, int J, int iters, float coeff, const int* rowptr, const int* col, const float* val, float* x,
+                       float* tmp, void* stream);
+
 /* batch_rodrigues (lbs.py:312-346): rot_vecs (n,3) -> rot_mats (n,3,3) */
 int g4d_batch_rodrigues(int n, const float* rot_vecs, float* rot_mats, void* stream);
 /* blend_shapes (smplx/smplx/lbs.py:288-309): betas (F,NB), shape_disps (V,3,NB) -> out (F,V,3) displacements */

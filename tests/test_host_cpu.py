@@ -337,3 +337,44 @@ def test_encoder_marks_the_fp_levels_that_feed_fused_gathers():
     from garment4d_b200.encoder import Pointnet2MSGSEG
     m = Pointnet2MSGSEG(input_channels=0, bn=True, global_feat=False)
     assert [fp.emit_point_major for fp in m.FP_modules] == [False, True, True]
+
+
+def _grid_adjacency(nu, nv):
+    idx = np.arange(nu * nv).reshape(nu, nv)
+    A = np.zeros((nu * nv, nu * nv), np.float32)
+    for a, b in ((idx[:-1, :].ravel(), idx[1:, :].ravel()), (idx[:, :-1].ravel(), idx[:, 1:].ravel()), (idx[:-1, :-1].ravel(), idx[1:, 1:].ravel())):
+        A[a, b] = 1
+        A[b, a] = 1
+    return A
+
+
+def test_smoothing_operator_is_row_normalised_adjacency_minus_identity():
+    """mesh_ops.smoothing_operator = pygcn/utils.py:56-63 normalize(adj_old) - eye (mesh_encoder.py:386), as CSR; dense, torch-sparse and
+    scipy inputs agree."""
+    import scipy.sparse as sp
+    import torch
+    from garment4d_b200 import mesh_ops
+    adj = _grid_adjacency(7, 5)
+    G = adj.shape[0]
+    want = np.diag(np.power(adj.sum(1), -1.0)) @ adj - np.eye(G, dtype=np.float32)
+    for inp in (sp.coo_matrix(adj), torch.from_numpy(adj), torch.from_numpy(adj).to_sparse()):
+        rp, c, v = (x.numpy() for x in mesh_ops.smoothing_operator(inp, "cpu"))
+        dense = np.zeros((G, G), np.float32)
+        for g in range(G):
+            dense[g, c[rp[g]:rp[g + 1]]] = v[rp[g]:rp[g + 1]]
+        assert np.allclose(dense, want, atol=1e-7)
+
+
+def test_oracle_knn_points_is_a_sorted_brute_force():
+    from oracle import mesh_ops as omesh
+    rs = np.random.RandomState(5)
+    p1, p2 = rs.randn(2, 40, 3).astype(np.float32), rs.randn(2, 90, 3).astype(np.float32)
+    p2[:, 50:60] = p2[:, :10]                                   # ties
+    d, i = omesh.knn_points(p1, p2, K=17)
+    for b in range(2):
+        full = ((p1[b][:, None].astype(np.float64) - p2[b][None].astype(np.float64)) ** 2).sum(-1)
+        assert np.allclose(d[b], np.sort(full, axis=1)[:, :17], rtol=1e-5, atol=1e-7)
+        assert (np.diff(d[b], axis=1) >= 0).all()
+        same = np.diff(d[b], axis=1) == 0
+        assert (np.diff(i[b], axis=1)[same] > 0).all()          # equal distances: ascending index
+        assert np.array_equal(np.take_along_axis(full, i[b], axis=1).astype(np.float32) >= 0, np.ones_like(d[b], bool))
