@@ -37,8 +37,7 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
     unsigned short* ks = reinterpret_cast<unsigned short*>(zs + PPT * T);   // original index of every point (n <= 8192)
     constexpr int NW = T / 32;
     __shared__ int slot_v[2][NW];
-    __shared__ unsigned slot_k[2][NW];
-    __shared__ float slot_p[2][NW][3];
+    __shared__ int slot_t[2][NW];                           // where the warp's candidate lives in xs/ys/zs/ks
     __shared__ float first_xyz[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t cloud = blockIdx.x;
@@ -87,12 +86,16 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
 
     // cached per-thread candidate and per-warp reduction
     float tmax = has_pts ? 1e10f : -1.f, thr = has_pts ? INFINITY : -1.f;
-    unsigned tkey = 0xFFFFFFFFu;
-    float bx = 0.f, by = 0.f, bz = 0.f;
+    int tpos = tid;                                        // position (slot * T + tid) of this thread's candidate
     int vb = __float_as_int(tmax), wv = 0;
     bool holder = false, stale_thr = false;
-    unsigned out_k = 0;
+    int out_i = 0;
     float out_x = 0.f, out_y = 0.f, out_z = 0.f;
+    // tie-break key of the point at a position: only needed when equal maxima meet (rare), so it is computed on demand
+    auto key_at = [&](int pos) -> unsigned {
+        const unsigned k = ks[pos];
+        return (__brev(k & bs_mask) & himask) | (k >> lg_bs);
+    };
 
     unsigned pf[2][8] = {}, pn[2] = {0, 0}, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
     for (int j = 1; j < m; ++j) {
@@ -126,18 +129,19 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
 #pragma unroll
                     for (int i = 0; i < w; ++i) em[i] |= em[i + w];
                 unsigned eq = em[0];
-                // candidate = smallest tie-break key among the clump's maximal points (almost always a single point)
-                unsigned mk = 0xFFFFFFFFu;
-                int bi = 0;
-                while (eq) {
-                    const int i = __ffs(eq) - 1;
-                    eq &= eq - 1;
-                    const unsigned k = ks[i * T + tid];
-                    const unsigned key = (__brev(k & bs_mask) & himask) | (k >> lg_bs);
-                    if (key < mk) { mk = key; bi = i; }
+                // candidate = the clump's maximal point; several equal maxima (rare): the smallest tie-break key
+                int bi = __ffs(eq) - 1;
+                if (eq & (eq - 1)) {
+                    unsigned mk = 0xFFFFFFFFu;
+                    while (eq) {
+                        const int i = __ffs(eq) - 1;
+                        eq &= eq - 1;
+                        const unsigned key = key_at(i * T + tid);
+                        if (key < mk) { mk = key; bi = i; }
+                    }
                 }
-                bx = xs[bi * T + tid]; by = ys[bi * T + tid]; bz = zs[bi * T + tid];
-                tmax = vmax; tkey = mk;
+                tpos = bi * T + tid;
+                tmax = vmax;
                 vb = __float_as_int(tmax);
                 stale_thr = true;
             }
@@ -147,16 +151,14 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
             const unsigned m1 = __ballot_sync(0xFFFFFFFFu, vb == wv);
             if (__popc(m1) == 1) holder = (vb == wv);
             else {
-                const unsigned wk = __reduce_min_sync(0xFFFFFFFFu, vb == wv ? tkey : 0xFFFFFFFFu);
+                const unsigned tkey = vb == wv ? key_at(tpos) : 0xFFFFFFFFu;
+                const unsigned wk = __reduce_min_sync(0xFFFFFFFFu, tkey);
                 holder = (vb == wv) && (tkey == wk);
             }
             if (PROF) c3 = clk();
         }
         const int par = j & 1;
-        if (holder) {                                      // cached between updates of this warp
-            slot_v[par][warp] = vb; slot_k[par][warp] = tkey;
-            slot_p[par][warp][0] = bx; slot_p[par][warp][1] = by; slot_p[par][warp][2] = bz;
-        }
+        if (holder) { slot_v[par][warp] = vb; slot_t[par][warp] = tpos; }      // cached between updates of this warp
         if (PROF) c4 = clk();
         __syncthreads();
         if (PROF) c5 = clk();
@@ -164,21 +166,22 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
         const int bv = __reduce_max_sync(0xFFFFFFFFu, sv);
         unsigned m2 = __ballot_sync(0xFFFFFFFFu, sv == bv);
         if (__popc(m2) > 1) {                              // equal maxima in several warps: smallest key wins
-            const unsigned sk = lane < NW ? slot_k[par][lane] : 0xFFFFFFFFu;
-            const unsigned bk2 = __reduce_min_sync(0xFFFFFFFFu, sv == bv ? sk : 0xFFFFFFFFu);
+            const unsigned sk = sv == bv ? key_at(slot_t[par][lane]) : 0xFFFFFFFFu;
+            const unsigned bk2 = __reduce_min_sync(0xFFFFFFFFu, sk);
             m2 = __ballot_sync(0xFFFFFFFFu, sv == bv && sk == bk2);
         }
         const int wl = __ffs(m2) - 1;
-        x1 = slot_p[par][wl][0]; y1 = slot_p[par][wl][1]; z1 = slot_p[par][wl][2];
+        const int wpos = slot_t[par][wl];
+        x1 = xs[wpos]; y1 = ys[wpos]; z1 = zs[wpos];
         if (PROF) { c6 = clk() + (__float_as_uint(x1) & 0u); }
         // Results are latched in the lanes of warp 0 and written out 32 steps at a time: a global store in every step
         // would make each barrier wait for its acknowledgement (BAR.SYNC drains the warp's outstanding stores).
         if (warp == 0) {
-            if (lane == (j & 31)) { out_k = slot_k[par][wl]; out_x = x1; out_y = y1; out_z = z1; }
+            if (lane == (j & 31)) { out_i = ks[wpos]; out_x = x1; out_y = y1; out_z = z1; }
             if ((j & 31) == 31 || j == m - 1) {
                 const int jj = (j & ~31) + lane;
                 if (jj >= 1 && jj <= j) {
-                    idx_out[jj] = (int)(((out_k & ~himask) << lg_bs) | __brev(out_k & himask));
+                    idx_out[jj] = out_i;
                     if (new_xyz) { new_xyz[3 * jj] = out_x; new_xyz[3 * jj + 1] = out_y; new_xyz[3 * jj + 2] = out_z; }
                 }
             }
