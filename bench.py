@@ -618,7 +618,7 @@ def kernel_breakdown(torch, L, model, pc, betas, pose, smpl, flush, peaks, C, N,
                     return gx if feats is None else torch.cat([gx, refgpu.grouping_operation(feats, idx)], dim=1)
                 hbm(f"query_and_group L{lvl} K={g.nsample}", ms,
                     12 * n_in + 12 * P + 4 * c_in * n_in + 4 * P * g.nsample + 4 * (c_in + 3) * P * g.nsample,
-                    ncu=[bq, ("group_fused_kernel", 2 * lvl + gi)], ref_ms=tref(ref_qg))
+                    ncu=[bq, ("group_fused_kernel", gi) if lvl == 0 else ("group_rows_kernel", 2 * (lvl - 1) + gi)], ref_ms=tref(ref_qg))
             new_xyz2, new_feats = sa(xyz, feats)
             feat_pm = None if feats is None else pu.point_major_of(feats)
             ctot = new_feats.shape[1]

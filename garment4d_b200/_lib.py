@@ -46,7 +46,6 @@ _SIGNATURES = {
     "g4d_three_interpolate_grad": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4d_fps_gather": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4d_ball_query2": (_i, [_i, _i, _i, _f, _i, _vp, _f, _i, _vp, _vp, _vp, _vp]),
-    "g4d_query_and_group": (_i, [_i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_group_fused": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_group_fused_pm": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_grid_bytes": (_sz, [_i, _i]),
@@ -55,6 +54,7 @@ _SIGNATURES = {
     "g4d_fps_workspace_bytes": (_sz, [_i, _i]),
     "g4d_fps_gather_ws": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4d_ball_query2_grid": (_i, [_i, _i, _i, _f, _i, _vp, _f, _i, _vp, _vp, _vp, _vp]),
+    "g4d_ball_query2_grid_ordered": (_i, [_i, _i, _i, _f, _i, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4d_three_nn_grid": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_sa_mlp_k0": (_i, [_i]),
     "g4d_sa_mlp_param_bytes": (_sz, [ctypes.POINTER(SaMlpDesc)]),

@@ -163,54 +163,6 @@ __global__ void group_points_grad_kernel(int c, int n, int ps, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused QueryAndGroup: scan -> idx rows live in shared memory -> grouped (3+C) x P x K tensor written once.
-// out layout = the reference's (B, 3+C, P, K) (use_xyz) or (B, C, P, K).
-
-template <int K>
-__global__ void __launch_bounds__(BQ_WARPS * 32)
-query_and_group_kernel(int n, int m, int c, float radius2, int use_xyz, const float* __restrict__ xyz_all,
-                       const float* __restrict__ new_xyz_all, const float* __restrict__ feat_all,
-                       int* __restrict__ idx_all, float* __restrict__ out_all) {
-    __shared__ float tile[BQ_TILE * 3];
-    __shared__ int sidx[BQ_QPB * K];
-    const size_t cloud = blockIdx.y;
-    const int q0 = blockIdx.x * BQ_QPB;
-    const int nq = min(BQ_QPB, m - q0);
-    const float* xyz = xyz_all + cloud * (size_t)n * 3;
-    const float* new_xyz = new_xyz_all + cloud * (size_t)m * 3;
-    for (int e = threadIdx.x; e < BQ_QPB * K; e += BQ_WARPS * 32) sidx[e] = 0;   // no-hit rows read as 0, like the zero-filled idx
-    __syncthreads();
-    BallScale sc[1];
-    sc[0].radius2 = radius2; sc[0].nsample = K;
-    sc[0].idx = sidx - (size_t)q0 * K;      // ball_scan indexes rows by absolute query id
-    ball_scan<1>(n, m, xyz, new_xyz, sc, q0, tile);
-    __syncthreads();
-
-    const int total = nq * K;               // contiguous (p,s) run of this CTA inside one channel plane
-    const size_t plane = (size_t)m * K;
-    const int cout = (use_xyz ? 3 : 0) + c;
-    float* out = out_all + cloud * (size_t)cout * plane + (size_t)q0 * K;
-    if (idx_all) {
-        int* gi = idx_all + cloud * plane + (size_t)q0 * K;
-        for (int e = threadIdx.x; e < total; e += BQ_WARPS * 32) gi[e] = sidx[e];
-    }
-    if (use_xyz) {
-        for (int e = threadIdx.x; e < total; e += BQ_WARPS * 32) {
-            const int src = sidx[e], q = e / K;
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-                out[d * plane + e] = __ldg(xyz + 3 * src + d) - __ldg(new_xyz + 3 * (q0 + q) + d);
-        }
-        out += 3 * plane;
-    }
-    if (c > 0) {
-        const float* feat = feat_all + cloud * (size_t)c * n;
-        for (int ci = 0; ci < c; ++ci)
-            for (int e = threadIdx.x; e < total; e += BQ_WARPS * 32)
-                out[ci * plane + e] = __ldg(feat + (size_t)ci * n + sidx[e]);
-    }
-}
-
 // Grouping stage of QueryAndGroup alone, given idx: (3+C) x P x K tensor written once with 16-byte stores; each thread owns
 // 4 consecutive samples of one centroid (its 4 source indices stay in registers) and walks a slab of channels.
 // Replaces grouping_operation(xyz) -> subtract -> grouping_operation(features) -> cat (pointnet2_utils.py:251-258).
@@ -365,32 +317,6 @@ G4D_API int g4d_group_points_grad(int b, int c, int n, int npoints, int nsample,
     if (ps > INT32_MAX) return bad_arg("group_points_grad: npoints*nsample exceeds int32");
     group_points_grad_kernel<<<chan_grid((int)ps, c, b), 256, 0, (cudaStream_t)stream>>>(c, n, (int)ps, grad_out, idx, grad_points);
     return finish_launch("g4d group_points_grad");
-}
-
-// Fused QueryAndGroup.forward (pointnet2_utils.py:243-265).  features may be null (c = 0, use_xyz must be 1).
-// idx (b,m,nsample) is optional output (rows with no hit are written as zeros here: the fused op owns the buffer).
-// out: (b, 3+c, m, nsample) if use_xyz else (b, c, m, nsample).
-G4D_API int g4d_query_and_group(int b, int n, int m, int c, float radius, int nsample, int use_xyz, const float* xyz,
-                                const float* new_xyz, const float* features, int* idx, float* out, void* stream) {
-    if (b < 0 || n <= 0 || m < 0 || c < 0) return bad_arg("query_and_group: bad size");
-    if (b == 0 || m == 0) return 0;
-    if (!xyz || !new_xyz || !out || (c > 0 && !features)) return bad_arg("query_and_group: null pointer");
-    if (c == 0 && !use_xyz) return bad_arg("query_and_group: no features and use_xyz = 0");
-    const float r2 = radius * radius;
-    dim3 grid((m + BQ_QPB - 1) / BQ_QPB, b);
-    cudaStream_t s = (cudaStream_t)stream;
-#define G4D_QG(KK) query_and_group_kernel<KK><<<grid, BQ_WARPS * 32, 0, s>>>(n, m, c, r2, use_xyz, xyz, new_xyz, features, idx, out)
-    switch (nsample) {
-        case 4: G4D_QG(4); break;
-        case 8: G4D_QG(8); break;
-        case 16: G4D_QG(16); break;
-        case 32: G4D_QG(32); break;
-        case 64: G4D_QG(64); break;
-        case 128: G4D_QG(128); break;
-        default: return bad_arg("query_and_group: nsample must be one of 4, 8, 16, 32, 64, 128");
-    }
-#undef G4D_QG
-    return finish_launch("g4d query_and_group");
 }
 
 // Grouping stage of QueryAndGroup.forward (pointnet2_utils.py:251-258) from a given idx (b,m,nsample), nsample % 4 == 0:

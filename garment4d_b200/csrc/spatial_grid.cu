@@ -131,7 +131,8 @@ constexpr int BQG_QPW = 4;
 template <int NS>
 __global__ void __launch_bounds__(BQG_WARPS * 32)
 ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_xyz_all, const float* __restrict__ grid_all,
-                       float r2_0, int K0, int* __restrict__ idx0_all, float r2_1, int K1, int* __restrict__ idx1_all) {
+                       const float* __restrict__ qgrid_all, float r2_0, int K0, int* __restrict__ idx0_all, float r2_1, int K1,
+                       int* __restrict__ idx1_all) {
     extern __shared__ unsigned bitmap_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t cloud = blockIdx.y;
@@ -139,6 +140,9 @@ ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_x
     const GridHdr H = *grid_hdr(g);
     const int* cell_start = grid_cell_start(g);
     const float4* sorted = grid_sorted(g);
+    // Optional processing order: the cell-sorted record of a grid built over the QUERIES, so that the queries of a block are spatial
+    // neighbours and their candidate runs hit L1 instead of L2 (FPS hands the centroids over in a far-apart order).
+    const float4* qsorted = qgrid_all ? grid_sorted(qgrid_all + cloud * grid_cloud_words(m)) : nullptr;
     unsigned* bm[2];
     bm[0] = bitmap_all + (size_t)warp * NS * nwords;
     bm[1] = bm[0] + nwords;
@@ -152,10 +156,17 @@ ball_query_grid_kernel(int n, int m, int nwords, const float* __restrict__ new_x
     const int wpl = (nwords + 31) / 32;      // bitmap words per lane (consecutive)
 
     for (int qi = 0; qi < BQG_QPW; ++qi) {
-        const int q = (blockIdx.x * BQG_WARPS + warp) * BQG_QPW + qi;
-        if (q >= m) break;                  // warp-uniform
-        const float* qp = new_xyz_all + (cloud * m + q) * 3;
-        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        const int qslot = (blockIdx.x * BQG_WARPS + warp) * BQG_QPW + qi;
+        if (qslot >= m) break;              // warp-uniform
+        int q = qslot;
+        float qx, qy, qz;
+        if (qsorted) {
+            const float4 qv = __ldg(qsorted + qslot);                  // (x, y, z, bits(query index)): the same floats as new_xyz[q]
+            qx = qv.x; qy = qv.y; qz = qv.z; q = __float_as_int(qv.w);
+        } else {
+            const float* qp = new_xyz_all + (cloud * m + q) * 3;
+            qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2);
+        }
         const int cx = cell_coord(qx, H.ox, H.inv_h, H.dx), cy = cell_coord(qy, H.oy, H.inv_h, H.dy), cz = cell_coord(qz, H.oz, H.inv_h, H.dz);
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, H.dx - 1);
         // The 27 neighbour cells are 9 contiguous runs of the sorted array (x is the fastest cell index).  Lanes 0..8
@@ -364,9 +375,10 @@ G4D_API int g4d_grid_build(int b, int n, const float* xyz, float min_cell, void*
 }
 
 // Same results as g4d_ball_query2 / g4d_ball_query (idx1 = NULL: one scale).  grid: g4d_grid_build over xyz with
-// min_cell >= max(radius0, radius1).  n <= 65536.
-G4D_API int g4d_ball_query2_grid(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
-                                 const float* new_xyz, const void* grid, void* stream) {
+// min_cell >= max(radius0, radius1).  n <= 65536.  query_grid (optional): g4d_grid_build over new_xyz (any cell size), used only
+// as a spatially coherent processing order of the queries.
+static int ball_query2_grid_impl(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
+                                 const float* new_xyz, const void* grid, const void* query_grid, void* stream) {
     if (b < 0 || n < 0 || m < 0 || nsample0 <= 0 || (idx1 && nsample1 <= 0)) return bad_arg("ball_query2_grid: bad size");
     if (b == 0 || m == 0 || n == 0) return 0;
     if (!new_xyz || !grid || !idx0) return bad_arg("ball_query2_grid: null pointer");
@@ -378,14 +390,25 @@ G4D_API int g4d_ball_query2_grid(int b, int n, int m, float radius0, int nsample
     cudaStream_t s = (cudaStream_t)stream;
     if (ns == 2) {
         if (smem > 32 * 1024) cudaFuncSetAttribute(ball_query_grid_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ball_query_grid_kernel<2><<<gridDim, BQG_WARPS * 32, smem, s>>>(n, m, nwords, new_xyz, (const float*)grid, radius0 * radius0, nsample0,
+        ball_query_grid_kernel<2><<<gridDim, BQG_WARPS * 32, smem, s>>>(n, m, nwords, new_xyz, (const float*)grid, (const float*)query_grid, radius0 * radius0, nsample0,
                                                                         idx0, radius1 * radius1, nsample1, idx1);
     } else {
         if (smem > 32 * 1024) cudaFuncSetAttribute(ball_query_grid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ball_query_grid_kernel<1><<<gridDim, BQG_WARPS * 32, smem, s>>>(n, m, nwords, new_xyz, (const float*)grid, radius0 * radius0, nsample0,
+        ball_query_grid_kernel<1><<<gridDim, BQG_WARPS * 32, smem, s>>>(n, m, nwords, new_xyz, (const float*)grid, (const float*)query_grid, radius0 * radius0, nsample0,
                                                                         idx0, 0.f, 1, nullptr);
     }
     return finish_launch("g4d ball_query2_grid");
+}
+
+G4D_API int g4d_ball_query2_grid(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
+                                 const float* new_xyz, const void* grid, void* stream) {
+    return ball_query2_grid_impl(b, n, m, radius0, nsample0, idx0, radius1, nsample1, idx1, new_xyz, grid, nullptr, stream);
+}
+
+G4D_API int g4d_ball_query2_grid_ordered(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1,
+                                         int* idx1, const float* new_xyz, const void* grid, const void* query_grid, void* stream) {
+    if (query_grid && ((uintptr_t)query_grid & 15)) return bad_arg("ball_query2_grid_ordered: misaligned query grid");
+    return ball_query2_grid_impl(b, n, m, radius0, nsample0, idx0, radius1, nsample1, idx1, new_xyz, grid, query_grid, stream);
 }
 
 // Same results as g4d_three_nn.  known_grid: g4d_grid_build over the KNOWN points (b,m,3) (any positive min_cell; a good

@@ -115,6 +115,9 @@ FPS_PRUNE_MIN_POINTS = 2048
 FPS_KERNEL = os.environ.get("G4D_FPS", "rows")
 
 
+QUERY_ORDER = os.environ.get("G4D_BQ_QUERY_ORDER", "1") != "0"
+
+
 def build_grid(xyz: torch.Tensor, min_cell: float) -> torch.Tensor:
     """Cell-sorted copy of every cloud (g4d_grid_build).  min_cell > 0: cell edge >= min_cell; min_cell <= -1: that many
     cells along the longest axis.  The grid is remembered on the tensor (``xyz._g4d_grid``) for later searches."""
@@ -353,9 +356,14 @@ def ball_query_pair(radius0, nsample0, radius1, nsample1, xyz, new_xyz):
         grid = _cached_grid(xyz, rmax)
         if grid is None:
             grid = build_grid(xyz, rmax)
-        rc = _lib.lib().g4d_ball_query2_grid(B, N, P, float(radius0), nsample0, _lib.ptr(idx0), float(radius1), nsample1,
-                                             _lib.ptr(idx1), _lib.ptr(new_xyz), _lib.ptr(grid), _lib.stream_ptr())
-        _lib.check(rc, "g4d_ball_query2_grid")
+        # FPS hands the centroids over far apart from one another: walk them in the cell order of a small grid of their own
+        qgrid = None
+        if QUERY_ORDER and P >= 256:
+            qgrid = _cached_grid(new_xyz) if _cached_grid(new_xyz) is not None else build_grid(new_xyz, rmax)
+        rc = _lib.lib().g4d_ball_query2_grid_ordered(B, N, P, float(radius0), nsample0, _lib.ptr(idx0), float(radius1), nsample1,
+                                                     _lib.ptr(idx1), _lib.ptr(new_xyz), _lib.ptr(grid),
+                                                     _lib.ptr(qgrid) if qgrid is not None else None, _lib.stream_ptr())
+        _lib.check(rc, "g4d_ball_query2_grid_ordered")
     else:
         rc = _lib.lib().g4d_ball_query2(B, N, P, float(radius0), nsample0, _lib.ptr(idx0), float(radius1), nsample1,
                                         _lib.ptr(idx1), _lib.ptr(new_xyz), _lib.ptr(xyz), _lib.stream_ptr())
@@ -367,7 +375,7 @@ _FUSED_NSAMPLE = (4, 8, 16, 32, 64, 128)
 
 
 class _QueryAndGroupFused(Function):
-    """QueryAndGroup.forward as ONE kernel.  Backward reproduces the reference graph: features and xyz receive the
+    """QueryAndGroup.forward as the ball query plus ONE grouping pass (nsample % 4 == 0).  Backward reproduces the reference graph: features and xyz receive the
     scatter-add of the grouped gradient (GroupingOperation.backward), new_xyz receives minus the sum over samples
     (the in-place ``grouped_xyz -= new_xyz`` of pointnet2_utils.py:253)."""
 
@@ -395,17 +403,12 @@ class _QueryAndGroupFused(Function):
             rc = _lib.lib().g4d_group_fused_pm(B, N, P, C, nsample, int(use_xyz), _lib.ptr(xyz), _lib.ptr(new_xyz),
                                                _lib.ptr(hit[0]), _lib.ptr(idx), _lib.ptr(out), _lib.stream_ptr())
             _lib.check(rc, "g4d_group_fused_pm")
-        elif nsample % 4 == 0:
+        else:
             # ball query (uniform grid for large clouds), then ONE grouping pass (16-byte stores) for xyz, features and the cat
             idx = BallQuery.apply(radius, nsample, xyz, new_xyz)
             rc = _lib.lib().g4d_group_fused(B, N, P, C, nsample, int(use_xyz), _lib.ptr(xyz), _lib.ptr(new_xyz),
                                             _lib.ptr(features), _lib.ptr(idx), _lib.ptr(out), _lib.stream_ptr())
             _lib.check(rc, "g4d_group_fused")
-        else:
-            idx = _i32(B, P, nsample, device=xyz.device)
-            rc = _lib.lib().g4d_query_and_group(B, N, P, C, float(radius), nsample, int(use_xyz), _lib.ptr(xyz), _lib.ptr(new_xyz),
-                                                _lib.ptr(features), _lib.ptr(idx), _lib.ptr(out), _lib.stream_ptr())
-            _lib.check(rc, "g4d_query_and_group")
         ctx.meta = (idx, N, C, use_xyz)
         return out
 

@@ -84,15 +84,10 @@ int g4d_fps_gather(int b, int n, int m, const float* xyz, int* idx, float* new_x
 int g4d_ball_query2(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
                     const float* new_xyz, const float* xyz, void* stream);
 
-/* QueryAndGroup.forward (pointnet2_utils.py:243-265) as one kernel: ball query + group(xyz) - centroid +
- * group(features) + cat.  features (b,c,n) may be NULL with c = 0.  out: (b, 3+c, m, nsample) when use_xyz,
- * else (b, c, m, nsample).  idx (b,m,nsample) optional output (no-hit rows written as zeros).
- * nsample in {4,8,16,32,64,128}. */
-int g4d_query_and_group(int b, int n, int m, int c, float radius, int nsample, int use_xyz, const float* xyz,
-                        const float* new_xyz, const float* features, int* idx, float* out, void* stream);
-
 /* Grouping stage of QueryAndGroup alone, from a given idx (b,m,nsample), nsample % 4 == 0: group(xyz) - centroid,
- * group(features) and the concatenation in one write pass (pointnet2_utils.py:251-258).  out as g4d_query_and_group. */
+ * group(features) and the concatenation in one write pass (pointnet2_utils.py:251-258); with g4d_ball_query[2][_grid] in front of it
+ * this is QueryAndGroup.forward (pointnet2_utils.py:243-265).  features (b,c,n) may be NULL with c = 0.
+ * out: (b, 3+c, m, nsample) when use_xyz, else (b, c, m, nsample). */
 int g4d_group_fused(int b, int n, int m, int c, int nsample, int use_xyz, const float* xyz, const float* new_xyz,
                     const float* features, const int* idx, float* out, void* stream);
 /* = g4d_group_fused with the features POINT-major, feat_pm (b, n, c) fp32 (c > 0): contiguous 256-byte gathers and a
@@ -118,6 +113,10 @@ int g4d_fps_gather_ws(int b, int n, int m, const float* xyz, int* idx, float* ne
 int g4d_ball_query2_grid(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
                          const float* new_xyz, const void* grid, void* stream);
 /* = g4d_three_nn given a grid over the KNOWN points; unknown_grid (optional) only fixes a coherent processing order */
+/* = g4d_ball_query2_grid; query_grid (optional): g4d_grid_build over new_xyz (b,m,3), any cell size -- only the processing order of
+ * the queries (spatial neighbours share a thread block, their candidate runs stay in L1). */
+int g4d_ball_query2_grid_ordered(int b, int n, int m, float radius0, int nsample0, int* idx0, float radius1, int nsample1, int* idx1,
+                                 const float* new_xyz, const void* grid, const void* query_grid, void* stream);
 int g4d_three_nn_grid(int b, int n, int m, const float* unknown, const void* known_grid, const void* unknown_grid,
                       float* dist2, int* idx, void* stream);
 

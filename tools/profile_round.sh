@@ -34,9 +34,9 @@ if [ "${SKIP_NCU:-0}" != 1 ]; then
       -k regex:'g4d::fp_interp_mlp' -f -o $OUT/${TAG}_full_fp python tools/ncu_once.py c3 > $OUT/${TAG}_full_fp_run.log 2>&1
   echo "ncu fp_interp_mlp exit $?"
   # launch list of the bench command (device time per launch; cold-cache, serialised: shares, not absolutes)
-  # (one frame group / stream: with several streams the 216 KB feature-propagation kernel failed to launch under ncu)
+  # (kernel by kernel, --no-graph: Nsight Compute cannot launch fp_mlp2_kernel from inside the captured graph)
   timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches.csv \
-      python bench.py --config c3 --chunks ${LAUNCH_CHUNKS:-1} --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-breakdown --no-train --no-extras > $OUT/${TAG}_launches_run.log 2>&1
+      python bench.py --config c3 --chunks ${LAUNCH_CHUNKS:-4} --no-graph --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-breakdown --no-train --no-extras > $OUT/${TAG}_launches_run.log 2>&1
   echo "ncu launches exit $?"
   python tools/summarize_launches.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.md 2>&1
   gzip -f $OUT/${TAG}_launches.csv
