@@ -333,7 +333,8 @@ fp_interp_mlp_kernel(const FpArgs a) {
         // =========================== CONSUMERS ==================================================================
         const int cg = warp >> 2;                                // consumer group; its warps own TMEM lane quadrants warp & 3
         const int row = (warp & 3) * 32 + lane;                  // tile row == TMEM lane
-        const bool issuer = (warp & 3) == 0 && lane == 0;
+        const bool iwarp = (warp & 3) == 0;                      // the group's MMA-issuing warp: converged code, one ELECTED lane issues
+        const bool issuer = iwarp && lane == 0;                  // (an `if (lane == 0)` around tcgen05.mma compiles to an ELECT + R2UR.BROADCAST loop per instruction)
         const uint32_t tacc = tmem + (uint32_t)cg * L.tcols;     // this group's accumulator columns
         const uint32_t lane_taddr = tacc + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t s_w1 = smem_u32(smem + L.off_w1), s_w2 = smem_u32(smem + L.off_w2), s_w3 = smem_u32(smem + L.off_w3),
@@ -354,12 +355,14 @@ fp_interp_mlp_kernel(const FpArgs a) {
             unsigned char* hbuf = smem + L.off_a + (size_t)ab * L.a_bytes;     // layer-1 operand, then (in place) the hidden activations
             const uint32_t s_h = smem_u32(hbuf);
             // ---- layer 1: A buffer -> D
-            if (issuer) {
+            if (iwarp) {
                 const long long tw0 = dbgc ? clock64() : 0;
                 mbar_wait_spin(bar_full + 8 * ab, use & 1);
                 if (dbgc) t_wait_full += clock64() - tw0;
-                fp_issue_layer(tacc, s_h, s_w1, L.c_in, L.c1);
-                umma_commit(my_done);
+                if (elect_one_sync()) {
+                    fp_issue_layer(tacc, s_h, s_w1, L.c_in, L.c1);
+                    umma_commit(my_done);
+                }
             }
             __syncwarp();
             { const long long tw0 = dbgc ? clock64() : 0;
@@ -369,7 +372,7 @@ fp_interp_mlp_kernel(const FpArgs a) {
             fp_epilogue_relu(lane_taddr, L.c1, b1, hbuf, row, nullptr, 0);
             tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
             // ---- layer 2 (FP output)
-            if (issuer) {
+            if (iwarp && elect_one_sync()) {
                 fp_issue_layer(tacc, s_h, s_w2, L.c1, L.c2);
                 if (!L.h1) umma_commit(bar_empty + 8 * ab);      // last reader of the buffer: back to the producers when it retires
                 umma_commit(my_done);
@@ -381,14 +384,14 @@ fp_interp_mlp_kernel(const FpArgs a) {
             tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
             if (L.h1) {
                 // ---- head layer 1
-                if (issuer) { fp_issue_layer(tacc, s_h, s_w3, L.c2, L.h1); umma_commit(my_done); }
+                if (iwarp && elect_one_sync()) { fp_issue_layer(tacc, s_h, s_w3, L.c2, L.h1); umma_commit(my_done); }
                 __syncwarp();
                 mbar_wait(my_done, phase); phase ^= 1;
                 tc_fence_after();
                 fp_epilogue_relu(lane_taddr, L.h1, b3, hbuf, row, nullptr, 0);
                 tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
                 // ---- head layer 2: logits, no activation
-                if (issuer) {
+                if (iwarp && elect_one_sync()) {
                     fp_issue_layer(tacc, s_h, s_w4, L.h1, L.h2p);
                     umma_commit(bar_empty + 8 * ab);             // last reader of the buffer: back to the producers when it retires
                     umma_commit(my_done);

@@ -286,7 +286,7 @@ def test_bench_reads_ncu_traffic_from_committed_profiles():
     rows = json.load(open(cands[-1]))
     for key in [("fps_pruned_kernel<512", 0), ("ball_query_grid_kernel<2>", 0), ("sa_mlp_max_kernel<32, 1, ", 1), ("fp_interp_mlp_kernel", 0),
                 ("three_nn_grid_kernel", 0), [("ball_query_grid_kernel<1>", 1), ("group_fused_kernel", 1)],
-                [("ball_query_kernel<1>", 3), ("group_fused_kernel", 5)]]:
+                [("ball_query_kernel<1>", 3), ("group_rows_kernel", 3)]]:
         v = bench.ncu_traffic(rows, key)
         assert v is not None and v > 0, key
     assert bench.ncu_traffic(rows, ("no_such_kernel", 0)) is None

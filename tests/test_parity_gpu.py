@@ -439,3 +439,24 @@ def test_group_all_equals_the_reference_views(cuda):
     with torch.no_grad():
         ref = torch.nn.functional.max_pool2d(sa.mlps[0](torch.from_numpy(want).to(cuda)), kernel_size=[1, 77]).squeeze(-1)
     assert torch.allclose(y, ref)
+
+
+@pytest.mark.parametrize("case", [(16, 4, 50), (17, 8, 33), (70, 16, 100), (96, 32, 256), (195, 64, 64), (130, 12, 7)], ids=lambda c: f"C{c[0]}K{c[1]}m{c[2]}")
+def test_query_and_group_from_point_major_rows(cuda, case):
+    """QueryAndGroup at feature levels (C >= 16) groups from a point-major copy of the features (g4d_group_fused_pm): channel counts
+    that are not multiples of 4 or 64, planes (m * K) that are not multiples of the 64-position tile, with and without xyz; and the
+    copy is refreshed when the features change in place."""
+    C, K, m = case
+    B, N, radius = 2, 700, 0.3
+    xyz = clouds(C + K, B, N, "body")
+    x = _t(xyz, cuda)
+    new_xyz = x[:, :m].contiguous()
+    feats = np.random.RandomState(C).randn(B, C, N).astype(np.float32)
+    f = _t(feats, cuda)
+    for use_xyz in (True, False):
+        got = pu.QueryAndGroup(radius, K, use_xyz=use_xyz)(x, new_xyz, f)
+        want = orc.query_and_group(radius, K, xyz, xyz[:, :m], feats, use_xyz=use_xyz)
+        assert np.array_equal(got.cpu().numpy(), want)
+    f.mul_(2.0)                                                   # in place: the remembered point-major copy is stale now
+    got = pu.QueryAndGroup(radius, K)(x, new_xyz, f)
+    assert np.array_equal(got.cpu().numpy(), orc.query_and_group(radius, K, xyz, xyz[:, :m], feats * np.float32(2.0), use_xyz=True))
