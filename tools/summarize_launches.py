@@ -39,7 +39,7 @@ def main(path):
         a[1] += r["us"]
     total = sum(a[1] for a in agg.values())
     ours = sum(a[1] for k, a in agg.items() if k.startswith("g4d::"))
-    print(f"# ncu launch list, one timed step of `bench.py` (c3: 240 frames, 4 frame groups): {len(step)} launches, "
+    print(f"# ncu launch list, one timed step of `bench.py` (c3: 240 frames, kernel by kernel without the CUDA graph; frame groups as given on the command line): {len(step)} launches, "
           f"{total:.0f} us serialised, {ours / total * 100:.1f} % in libgarment4d_b200 kernels "
           f"({sum(a[0] for k, a in agg.items() if k.startswith('g4d::'))} launches)\n")
     print("| kernel | launches | total us | share | block | grid (first launch) |")
