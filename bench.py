@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {  # name: (B, T, N)   BASELINE.json configs[1..4]
     "c2": (8, 1, 8192), "c3": (8, 30, 8192), "c4": (32, 30, 8192), "c5": (64, 30, 16384),
+    "c4_8": (4, 30, 8192),      # (not a BASELINE config: one rank's share of c4 at 8 GPUs, for single-GPU experiments)
 }
 V_SMPL = 6890
 METRIC = "frames/sec (B*T*N pts) encoder+LBS fwd"

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "g4d_grid_bytes": (_sz, [_i, _i]),
     "g4d_grid_build": (_i, [_i, _i, _vp, _f, _vp, _vp]),
     "g4d_fps_gather_grid": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "g4d_fps_concurrency_hint": (None, [_i]),
     "g4d_fps_workspace_bytes": (_sz, [_i, _i]),
     "g4d_fps_gather_ws": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "g4d_ball_query2_grid": (_i, [_i, _i, _i, _f, _i, _vp, _f, _i, _vp, _vp, _vp, _vp]),

@@ -208,6 +208,8 @@ fps_pruned_kernel(int n, int m, int lg_bs, const float4* __restrict__ sorted_all
     }
 }
 
+static int g_fps_step_clouds = 0;      // g4d_fps_concurrency_hint
+
 template <int T, int PPT, bool PROF = false>
 static int launch_fps_pruned(int b, int n, int m, int lg, const float4* sorted, long long stride, int* idx, float* new_xyz, cudaStream_t s) {
     auto kern = fps_pruned_kernel<T, PPT, PROF>;
@@ -227,20 +229,26 @@ int fps_pruned_sorted(int b, int n, int m, const float4* sorted, long long strid
     if (n <= 1024) return launch_fps_pruned<128, 8>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
     if (n <= 2048) return launch_fps_pruned<128, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
     if (n <= 4096) return launch_fps_pruned<256, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
-    // G4D_FPS_WIDE=1: 1024 threads x 8 points per cloud (half the update path per step, one CTA per SM).  Measured on B200 at
-    // 8192 -> 1024: 0.78 ms for <= 148 clouds against 0.79 ms for the 512 x 16 form, and 1.52 ms against 1.01 ms at 240 clouds
-    // (two waves instead of two clouds per SM): not worth a heuristic, off unless asked for.
-    static const int wide_env = getenv("G4D_FPS_WIDE") ? atoi(getenv("G4D_FPS_WIDE")) : 0;
-    const bool wide = wide_env != 0;
-    if (wide) return launch_fps_pruned<1024, 8>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
+    // 1024 threads x 8 points per cloud (half the update path per step, but one CTA per SM): 0.65 ms against 0.71 ms for the
+    // 512 x 16 form when every cloud of the step has an SM to itself, 1.27 ms against 0.92 ms when they do not (two waves instead
+    // of two clouds per SM).  A launch cannot see the launches on other streams, so the caller says how many clouds the whole
+    // step holds (g4d_fps_concurrency_hint); without a hint the launch's own count decides.  G4D_FPS_WIDE=0/1 forces the choice.
+    static const int wide_env = getenv("G4D_FPS_WIDE") ? atoi(getenv("G4D_FPS_WIDE")) : -1;
+    const int step_clouds = g_fps_step_clouds > 0 ? g_fps_step_clouds : b;
+    const bool wide = wide_env >= 0 ? wide_env != 0 : step_clouds <= sm_count();
     static const bool prof = getenv("G4D_FPS_PROF") != nullptr;
     if (prof) return launch_fps_pruned<512, 16, true>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
+    if (wide) return launch_fps_pruned<1024, 8>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
     return launch_fps_pruned<512, 16>(b, n, m, lg, sorted, stride, idx, new_xyz, s);
 }
 
 }  // namespace g4d
 
 using namespace g4d;
+
+// How many clouds the caller's whole step samples concurrently (all streams together); 0 = unknown (each launch decides from its own
+// count).  Only steers the choice between the two pruned-FPS kernel shapes: results never depend on it.
+G4D_API void g4d_fps_concurrency_hint(int step_clouds) { g_fps_step_clouds = step_clouds > 0 ? step_clouds : 0; }
 
 // Measurement aid: phase sums written by the last G4D_FPS_PROF=1 launch (32 warps x 20 words), see tools/fps_phases.py.
 G4D_API int g4d_debug_fps_phases(unsigned* out640) {

@@ -37,6 +37,7 @@ class EncoderLBSRunner:
     def forward_device(self, pc, betas, pose):
         """Inputs resident on the device.  Returns (sem_logits (C,N,classes), verts (C,V,3), joints (C,J,3))."""
         C = pc.shape[0]
+        _lib.lib().g4d_fps_concurrency_hint(int(C))              # the frame groups' FPS launches share the GPU: C clouds at once
         cur = torch.cuda.current_stream(self.device)
         sems = []
         capturing = torch.cuda.is_current_stream_capturing()
@@ -55,6 +56,7 @@ class EncoderLBSRunner:
         for st in self.streams:
             cur.wait_stream(st)
         cur.wait_stream(self.lbs_stream)
+        _lib.lib().g4d_fps_concurrency_hint(0)
         return torch.cat(sems), verts, joints
 
     @torch.no_grad()
@@ -64,6 +66,7 @@ class EncoderLBSRunner:
         lbs stream, overlapped with the encoder.  Asynchronous: synchronise the current stream (or the device) before reading
         the outputs."""
         C = pc_pin.shape[0]
+        _lib.lib().g4d_fps_concurrency_hint(int(C))
         cur = torch.cuda.current_stream(self.device)
         self.lbs_stream.wait_stream(cur)
         with torch.cuda.stream(self.lbs_stream):
@@ -81,6 +84,7 @@ class EncoderLBSRunner:
         for st in self.streams:
             cur.wait_stream(st)
         cur.wait_stream(self.lbs_stream)
+        _lib.lib().g4d_fps_concurrency_hint(0)
 
 
 class GraphedEncoderLBSRunner(EncoderLBSRunner):

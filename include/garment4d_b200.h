@@ -107,6 +107,9 @@ int g4d_fps_gather_grid(int b, int n, int m, const void* grid, int* idx, float* 
  * first sorted by the 15-bit Morton code of a 32^3 grid over its bounding cube, 32 consecutive points form a clump that all
  * 32 lanes of a warp update together.  1 <= n <= 16384.  workspace: device buffer of g4d_fps_workspace_bytes(b, n),
  * 16-byte aligned (the sorted copy; scratch). */
+/* optional: number of clouds the caller's whole step samples concurrently over all its streams (0 = unknown); steers the kernel
+ * shape of g4d_fps_gather_ws / g4d_fps_gather_grid only, never the results */
+void g4d_fps_concurrency_hint(int step_clouds);
 size_t g4d_fps_workspace_bytes(int b, int n);
 int g4d_fps_gather_ws(int b, int n, int m, const float* xyz, int* idx, float* new_xyz, void* workspace, void* stream);
 /* = g4d_ball_query2 (idx1 = NULL: = g4d_ball_query) given a grid over xyz with min_cell >= max radius; n <= 65536 */

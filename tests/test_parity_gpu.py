@@ -460,3 +460,22 @@ def test_query_and_group_from_point_major_rows(cuda, case):
     f.mul_(2.0)                                                   # in place: the remembered point-major copy is stale now
     got = pu.QueryAndGroup(radius, K)(x, new_xyz, f)
     assert np.array_equal(got.cpu().numpy(), orc.query_and_group(radius, K, xyz, xyz[:, :m], feats * np.float32(2.0), use_xyz=True))
+
+
+@pytest.mark.parametrize("kind", ["cube", "body"])
+def test_fps_both_kernel_shapes_give_the_reference_indices(cuda, kind):
+    """The pruned FPS has two shapes (1024 threads x 8 points when every cloud of the step gets an SM, 512 x 16 otherwise); the
+    caller's concurrency hint picks one, the indices never change."""
+    from garment4d_b200 import _lib
+    xyz = clouds(31, 3, 8192, kind)
+    x = _t(xyz, cuda)
+    want = orc.furthest_point_sample(xyz, 300)
+    L = _lib.lib()
+    try:
+        for hint in (1, 100000):                                   # few clouds -> wide shape; many -> two clouds per SM
+            L.g4d_fps_concurrency_hint(hint)
+            idx, new_xyz = pu.furthest_point_sample_and_gather(x, 300)
+            assert np.array_equal(idx.cpu().numpy(), want), f"hint {hint}"
+            assert np.array_equal(new_xyz.cpu().numpy(), np.take_along_axis(xyz, want[:, :, None].astype(np.int64).repeat(3, 2), axis=1))
+    finally:
+        L.g4d_fps_concurrency_hint(0)
