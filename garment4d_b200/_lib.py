@@ -68,6 +68,7 @@ _SIGNATURES = {
     "g4d_fp_param_bytes": (_sz, [ctypes.POINTER(FpDesc)]),
     "g4d_fp_pack_params": (_i, [ctypes.POINTER(FpDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_fp_interp_mlp": (_i, [ctypes.POINTER(FpDesc), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "g4d_fp_interp_mlp_labels": (_i, [ctypes.POINTER(FpDesc), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4d_mlp2_param_bytes": (_sz, [ctypes.POINTER(Mlp2Desc)]),
     "g4d_mlp2_pack_params": (_i, [ctypes.POINTER(Mlp2Desc), _vp, _vp, _vp, _vp, _vp]),
     "g4d_mlp2_rows": (_i, [ctypes.POINTER(Mlp2Desc), _vp, _i, _i, _vp, _vp, _vp, _vp]),

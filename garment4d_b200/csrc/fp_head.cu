@@ -100,6 +100,7 @@ struct FpArgs {
     const unsigned char* params;
     float* out_feat;             // (b, c2, n) channel-major fp32
     float* out_head;             // (b, n, h2) or null
+    unsigned char* out_label;    // (b, n) arg-max over the h2 head outputs, or null
     long long* dbg;              // optional cycle counters of CTA 0 (g4d_debug_fp_counters)
 };
 
@@ -403,9 +404,17 @@ fp_interp_mlp_kernel(const FpArgs a) {
                 tmem_ld16(lane_taddr, v);
                 if (live) {
                     float* o = a.out_head + (size_t)R * L.h2;
+                    float best = 0.f;
+                    int lab = 0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (j < L.h2) o[j] = v[j] + b4[j];
+                        if (j < L.h2) {
+                            const float z = v[j] + b4[j];
+                            o[j] = z;
+                            // torch.argmax: the first maximal class, NaN counts as the maximum (mesh_encoder.py:113)
+                            if (j == 0 || z > best || (z != z && best == best)) { best = z; lab = j; }
+                        }
+                    if (a.out_label) a.out_label[R] = (unsigned char)lab;
                 }
                 tc_fence_before(); group_bar(bar_id);            // every warp has drained D: the next tile's layer 1 may overwrite it
             }
@@ -461,8 +470,8 @@ G4D_API int g4d_fp_pack_params(const g4d_fp_desc* d, const float* w1, const floa
     return 0;
 }
 
-G4D_API int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int b, int n, int m, const float* dist2, const int* idx,
-                              const void* known_pm, float* out_feat, float* out_head, void* stream) {
+static int fp_interp_mlp_impl(const g4d_fp_desc* d, const void* params_dev, int b, int n, int m, const float* dist2, const int* idx,
+                              const void* known_pm, float* out_feat, float* out_head, unsigned char* out_label, void* stream) {
     FpArgs a;
     const char* why = nullptr;
     if (!d || !fp_layout(d, &a.L, &why)) return bad_arg(why ? why : "fp: null descriptor");
@@ -477,7 +486,7 @@ G4D_API int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int 
     if (nt > INT32_MAX) return bad_arg("fp_interp_mlp: too many tiles");
     a.ntiles = (int)nt;
     a.dist2 = dist2; a.idx = idx; a.known_pm = (const __half*)known_pm; a.params = (const unsigned char*)params_dev;
-    a.out_feat = out_feat; a.out_head = out_head;
+    a.out_feat = out_feat; a.out_head = out_head; a.out_label = a.L.h1 ? out_label : nullptr;
     a.dbg = g_fp_dbg;
     cudaError_t e = cudaFuncSetAttribute(fp_interp_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.L.total_smem);
     if (e != cudaSuccess) { set_error("fp_interp_mlp: shared memory opt-in (%u B): %s", a.L.total_smem, cudaGetErrorString(e)); return (int)e; }
@@ -486,4 +495,18 @@ G4D_API int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int 
     if (grid > a.ntiles) grid = a.ntiles;
     fp_interp_mlp_kernel<<<(unsigned)grid, FP_THREADS, a.L.total_smem, (cudaStream_t)stream>>>(a);
     return finish_launch("g4d fp_interp_mlp");
+}
+
+G4D_API int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int b, int n, int m, const float* dist2, const int* idx,
+                              const void* known_pm, float* out_feat, float* out_head, void* stream) {
+    return fp_interp_mlp_impl(d, params_dev, b, n, m, dist2, idx, known_pm, out_feat, out_head, nullptr, stream);
+}
+
+// = g4d_fp_interp_mlp, and out_label (b, n) uint8 = argmax over the head's outputs of every point (torch.argmax semantics: first
+// maximal class), written by the last epilogue: the segmentation the model consumes (modules/mesh_encoder.py:113).
+G4D_API int g4d_fp_interp_mlp_labels(const g4d_fp_desc* d, const void* params_dev, int b, int n, int m, const float* dist2,
+                                     const int* idx, const void* known_pm, float* out_feat, float* out_head,
+                                     unsigned char* out_label, void* stream) {
+    if (d && d->h1 && !out_label) return bad_arg("fp_interp_mlp_labels: null label pointer");
+    return fp_interp_mlp_impl(d, params_dev, b, n, m, dist2, idx, known_pm, out_feat, out_head, out_label, stream);
 }

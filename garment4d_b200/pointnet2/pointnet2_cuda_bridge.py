@@ -66,7 +66,8 @@ def pack_fp_head(fp_mlp, fc_layer, device):
 
 
 def fp_interp_mlp(packed, unknown, known, known_feats):
-    """unknown (B,n,3), known (B,m,3), known_feats (B,C,m) fp32 -> (features (B,c2,n) fp32, logits (B,n,h2) fp32)."""
+    """unknown (B,n,3), known (B,m,3), known_feats (B,C,m) fp32 -> (features (B,c2,n) fp32, logits (B,n,h2) fp32).
+    The kernel's last epilogue also writes the arg-max labels (B,n) uint8; they ride on the logits tensor (segmentation_labels())."""
     from .pointnet2_utils import three_nn_raw, point_major_of
     unknown = unknown if unknown.is_contiguous() else unknown.contiguous()
     known = known if known.is_contiguous() else known.contiguous()
@@ -80,7 +81,21 @@ def fp_interp_mlp(packed, unknown, known, known_feats):
         known_pm = known_feats.detach().transpose(1, 2).to(torch.float16).contiguous()
     feat = torch.empty(B, packed.c2, n, dtype=torch.float32, device=unknown.device)
     logits = torch.empty(B, n, packed.h2, dtype=torch.float32, device=unknown.device)
-    rc = _lib.lib().g4d_fp_interp_mlp(ctypes.byref(packed.desc), _lib.ptr(packed.params), B, n, m, _lib.ptr(dist2), _lib.ptr(idx),
-                                      _lib.ptr(known_pm), _lib.ptr(feat), _lib.ptr(logits), _lib.stream_ptr())
-    _lib.check(rc, "g4d_fp_interp_mlp")
+    labels = torch.empty(B, n, dtype=torch.uint8, device=unknown.device)
+    rc = _lib.lib().g4d_fp_interp_mlp_labels(ctypes.byref(packed.desc), _lib.ptr(packed.params), B, n, m, _lib.ptr(dist2), _lib.ptr(idx),
+                                             _lib.ptr(known_pm), _lib.ptr(feat), _lib.ptr(logits), _lib.ptr(labels), _lib.stream_ptr())
+    _lib.check(rc, "g4d_fp_interp_mlp_labels")
+    try:
+        logits._g4d_labels = (labels, logits._version)
+    except Exception:
+        pass
     return feat, logits
+
+
+def segmentation_labels(sem_logits):
+    """argmax(sem_logits, dim=2) as uint8 (mesh_encoder.py:113): the labels the fused head kernel wrote next to these logits when
+    they are still current, otherwise computed here."""
+    hit = getattr(sem_logits, "_g4d_labels", None)
+    if hit is not None and hit[1] == sem_logits._version and hit[0].shape == sem_logits.shape[:2]:
+        return hit[0]
+    return sem_logits.argmax(dim=2).to(torch.uint8)

@@ -9,6 +9,7 @@ import torch
 
 from . import _lib
 from . import lbs as glbs
+from .pointnet2 import pointnet2_cuda_bridge as _bridge
 
 
 class EncoderLBSRunner:
@@ -80,7 +81,8 @@ class EncoderLBSRunner:
             with torch.cuda.stream(st):
                 pc = pc_pin[lo:hi].to(self.device, non_blocking=True)
                 _, sem, _, _ = self.model(pc)
-                labels_pin[lo:hi].copy_(sem.argmax(dim=2).to(torch.uint8), non_blocking=True)   # the segmentation the model consumes (mesh_encoder.py:113)
+                # the segmentation the model consumes (mesh_encoder.py:113): written by the head kernel's last epilogue
+                labels_pin[lo:hi].copy_(_bridge.segmentation_labels(sem), non_blocking=True)
         for st in self.streams:
             cur.wait_stream(st)
         cur.wait_stream(self.lbs_stream)

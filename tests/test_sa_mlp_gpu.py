@@ -124,6 +124,15 @@ def test_fused_fp0_head_vs_modules(cuda, N):
     # 7 chained fp16-operand layers (3 SA + 2 FP + 2 head) end to end, FP1/FP2 through TF32 cuDNN: 5e-3 of the range
     _close(lf[0], lf_ref[0], tol=5e-3)
     _close(sem, sem_ref, tol=5e-3)
+    # the head kernel's last epilogue also wrote the arg-max labels (mesh_encoder.py:113); they are dropped once the logits change
+    from garment4d_b200.pointnet2.pointnet2_cuda_bridge import segmentation_labels
+    assert getattr(sem, "_g4d_labels", None) is not None
+    lab = segmentation_labels(sem)
+    assert lab.dtype == torch.uint8 and lab.data_ptr() == sem._g4d_labels[0].data_ptr()
+    assert torch.equal(lab, sem.argmax(dim=2).to(torch.uint8))
+    sem[:, :, 3] += 100.0
+    lab2 = segmentation_labels(sem)
+    assert lab2.data_ptr() != lab.data_ptr() and bool((lab2 == 3).all())
 
 
 @pytest.mark.parametrize("spec", [(1024, 256, 256, 96, [352, 256, 128]), (256, 64, 384, 192, [576, 512, 256]), (300, 41, 16, 0, [16, 24])],
