@@ -403,6 +403,8 @@ fp_interp_mlp_kernel(const FpArgs a) {
                 float v[16];
                 tmem_ld16(lane_taddr, v);
                 if (live) {
+                    // (staging these h2 floats per row through shared memory for fully coalesced stores was measured: 0.448 -> 0.477 ms.
+                    // The kernel is bound by the latency of this consumer chain, not by store sectors.)
                     float* o = a.out_head + (size_t)R * L.h2;
                     float best = 0.f;
                     int lab = 0;
