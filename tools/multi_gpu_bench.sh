@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
-# Runs ON THE GPU BOX with N GPUs: the multi-GPU bench exactly as the driver launches it, with NCCL logging. usage: r02c.sh TAG N [extra bench args]
+# Runs ON THE GPU BOX with N GPUs: the multi-GPU bench exactly as the driver launches it, with NCCL logging. usage: multi_gpu_bench.sh TAG N [extra bench args]
 set -u
-TAG="${1:-r02c}"; N="${2:-2}"; shift; shift
+TAG="${1:-mgpu}"; N="${2:-2}"; shift; shift
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi topo -m > $OUT/${TAG}_topo.txt 2>&1
 export NCCL_DEBUG=INFO NCCL_DEBUG_FILE=$PWD/$OUT/${TAG}_nccl_%h_%p.log TORCH_NCCL_TRACE_BUFFER_SIZE=2000 TORCH_NCCL_DUMP_ON_TIMEOUT=1
