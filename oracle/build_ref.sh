@@ -16,14 +16,19 @@ if [ ! -d "$REF" ]; then
     exit 0
 fi
 mkdir -p "$OUT"
-# The reference's own Python operator layer (pointnet2_utils.py, pointnet2_modules.py, pytorch_utils.py), unmodified, next to its
-# kernels: tests/test_reference_layer_gpu.py imports it ON TOP OF the repository's pointnet2_cuda.py to show the drop-in boundary
-# holds (the GPU box has no /root/reference; like the .so, this copy is test infrastructure, git-ignored, never part of the product).
-mkdir -p "$OUT/pointnet2"
-for f in __init__.py pointnet2_utils.py pointnet2_modules.py pytorch_utils.py; do
-    [ -f "$REF/../$f" ] && cp -f "$REF/../$f" "$OUT/pointnet2/$f" && chmod u+w "$OUT/pointnet2/$f"
-done
-[ -f "$OUT/pointnet2/__init__.py" ] || : > "$OUT/pointnet2/__init__.py"
+# The reference's own Python operator layer (pointnet2_utils.py, pointnet2_modules.py, pytorch_utils.py), unmodified, as ONE
+# archive next to its kernels: tests/test_reference_layer_gpu.py puts the archive on sys.path (zipimport) ON TOP OF the repository's
+# pointnet2_cuda.py to show the drop-in boundary holds.  The GPU box has no /root/reference; like the .so, the archive is a build
+# product of the reference made by this recipe: test infrastructure, git-ignored, never part of the product, no loose copies.
+rm -rf "$OUT/pointnet2"
+"${PYTHON:-python}" - "$REF/.." "$OUT/pointnet2_reference_layer.zip" <<'EOF'
+import os, sys, zipfile
+src, dst = sys.argv[1], sys.argv[2]
+with zipfile.ZipFile(dst, "w", zipfile.ZIP_DEFLATED) as z:
+    z.writestr("pointnet2/__init__.py", "")
+    for f in ("pointnet2_utils.py", "pointnet2_modules.py", "pytorch_utils.py"):
+        z.write(os.path.join(src, f), "pointnet2/" + f)
+EOF
 if [ "$OUT/libpointnet2_ref.so" -nt "$HERE/ref_shim.cu" ] && [ "${1:-}" != "--force" ]; then
     echo "build_ref.sh: $OUT/libpointnet2_ref.so up to date"; exit 0
 fi

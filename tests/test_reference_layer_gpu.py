@@ -1,8 +1,8 @@
 """-m gpu: the drop-in boundary, shown with the reference's OWN Python operator layer.
 
-oracle/build_ref.sh stages the reference's unmodified ``pointnet2_utils.py`` / ``pointnet2_modules.py`` / ``pytorch_utils.py``
-under oracle/_ref/pointnet2/ (git-ignored test infrastructure, like the reference kernels next to it; the GPU box has no
-/root/reference).  They do ``import pointnet2_cuda as pointnet2`` (pointnet2_utils.py:7): with the repository root on sys.path
+oracle/build_ref.sh packs the reference's unmodified ``pointnet2_utils.py`` / ``pointnet2_modules.py`` / ``pytorch_utils.py``
+into oracle/_ref/pointnet2_reference_layer.zip (git-ignored test infrastructure, like the reference kernels next to it; the GPU
+box has no /root/reference); the archive goes on sys.path (zipimport).  They do ``import pointnet2_cuda as pointnet2`` (pointnet2_utils.py:7): with the repository root on sys.path
 that resolves to the repository's top-level ``pointnet2_cuda.py``, i.e. the B200 kernels behind the reference's nine-function
 extension API.  Results are compared with the CPU oracle (bit-exact for indices) and with this repository's own operator layer.
 """
@@ -19,13 +19,13 @@ from tests.util import clouds
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_PKG = os.path.join(ROOT, "oracle", "_ref")
+REF_PKG = os.path.join(ROOT, "oracle", "_ref", "pointnet2_reference_layer.zip")
 
 
 @pytest.fixture(scope="module")
 def ref_layer():
-    if not os.path.exists(os.path.join(REF_PKG, "pointnet2", "pointnet2_utils.py")):
-        pytest.skip("oracle/_ref/pointnet2 was not staged (oracle/build_ref.sh needs /root/reference)")
+    if not os.path.exists(REF_PKG):
+        pytest.skip("oracle/_ref/pointnet2_reference_layer.zip was not built (oracle/build_ref.sh needs /root/reference)")
     sys.path.insert(0, REF_PKG)
     try:
         import pointnet2_cuda                                     # the repository's shim, found through ROOT on sys.path
