@@ -10,10 +10,13 @@
 //
 // The weights do not fit shared memory (FP2: 590 + 262 KB), so both GEMMs run a K-loop over STAGES (32 or 16 channels) of a ring:
 //   stage = [A: 128 rows x ks k fp16, canonical K-major | W: N rows x ks k, canonical]
-//   loader (1 lane)        per stage ONE TMA tensor copy for A -- the activation matrix seen as a 3-D tensor
-//                          (8 channels, rows, c_in / 8) with box (8, 128, ks / 8), which lands as [k/8][row][k%8] = the UMMA
-//                          canonical no-swizzle K-major image; rows past the end are zero-filled by the hardware -- and one
-//                          cp.async.bulk for the host-packed W stage, both completing on the stage's full barrier (expect_tx).
+//   loader (1 lane)        per stage ONE TMA tensor copy for A -- box (ks channels, 128 rows) of the (rows, c_in) activation matrix
+//                          with the hardware swizzle whose span is the box row (ks = 64: SWIZZLE_128B), read by the MMA through a
+//                          K-major descriptor of the same swizzle mode; rows and channels past the end are zero-filled by the
+//                          hardware -- and one cp.async.bulk for the host-packed W stage (canonical no-swizzle image), both
+//                          completing on the stage's full barrier (expect_tx).  (A first version fetched A as a 3-D box with
+//                          16-byte inner rows straight into the no-swizzle layout: 1024 row requests per 16 KB made the TMA unit
+//                          the bottleneck of the whole kernel.)
 //                          In layer 2 the A operand is the hidden activation H, resident in shared memory: W only.
 //   MMA issuer (1 warp)    warp-uniform code, elected lane: per stage ks/16 k-steps x (N / 256 rounded up) tcgen05.mma, then
 //                          tcgen05.commit -> the stage's empty barrier; D1 [128 x c1] and D2 [128 x c2] in TMEM, in SEPARATE
@@ -61,23 +64,25 @@ static bool mlp2_layout(const g4d_mlp2_desc* d, Mlp2Layout* L, const char** why)
     L->c1p = d->c1 / L->npass;
     L->off_bias = 0;                                    // b1 | b2 (fp32) at the start of shared memory
     L->off_h = ((uint32_t)(d->c1 + d->c2) * 4 + 127) / 128 * 128;
-    L->off_ring = L->off_h + (uint32_t)M2_TILE * L->c1p * 2;
+    L->off_ring = (L->off_h + (uint32_t)M2_TILE * L->c1p * 2 + 1023u) / 1024u * 1024u;      // swizzled A stages: 1024-byte aligned
     const uint32_t budget = 227u * 1024u - 1024u - 512u;
-    int ks = 32, nst = 0;
-    for (;; ks = 16) {                                  // 32 channels per stage unless that leaves fewer than 3 ring slots
-        const uint32_t wmax = (uint32_t)(L->c1p > d->c2 ? L->c1p : d->c2) * ks * 2;
-        L->a_bytes = (uint32_t)M2_TILE * ks * 2;
-        L->stage_bytes = L->a_bytes + wmax;
-        if (L->off_ring + 2u * L->stage_bytes + M2_BAR_BYTES > budget) {
-            if (ks == 16) { *why = "mlp2: shared memory footprint exceeds 227 KB"; return false; }
-            continue;
-        }
-        nst = (int)((budget - M2_BAR_BYTES - L->off_ring) / L->stage_bytes);
-        if (nst >= 3 || ks == 16) break;
+    // Channels per stage: as many as leave three ring slots.  Every stage costs the issuer ~500 cycles of waits, fences and commits
+    // whatever it holds, and a 128 x 256 x 16 MMA runs 128 cycles (tools/microbench/mma_rate.cu: the full 8192 FLOP/cycle/SM from this
+    // layout, ring and concurrent bulk copies included): 64 channels = 4 MMAs per stage keep the tensor pipe, not the issuer, busy.
+    static const int ks_env = getenv("G4D_MLP2_KS") ? atoi(getenv("G4D_MLP2_KS")) : 0;
+    int ks = 0, nst = 0;
+    for (int cand = 64; cand >= 16; cand >>= 1) {
+        if (ks_env && cand != ks_env) continue;
+        const uint32_t wmax = (uint32_t)(L->c1p > d->c2 ? L->c1p : d->c2) * cand * 2;
+        const uint32_t a_bytes = (uint32_t)M2_TILE * cand * 2, stage = (a_bytes + wmax + 1023u) / 1024u * 1024u;
+        if (L->off_ring + 2u * stage + M2_BAR_BYTES > budget) continue;
+        const int n = (int)((budget - M2_BAR_BYTES - L->off_ring) / stage);
+        if (n >= 3 || cand == 16 || ks_env) { ks = cand; nst = n; L->a_bytes = a_bytes; L->stage_bytes = stage; break; }
     }
+    if (!ks) { *why = "mlp2: shared memory footprint exceeds 227 KB"; return false; }
     if (nst > M2_MAX_STAGES) nst = M2_MAX_STAGES;
     L->ks = ks; L->nst = nst;
-    L->n1 = d->c_in / ks; L->n2 = L->c1p / ks;          // stages per PASS
+    L->n1 = (d->c_in + ks - 1) / ks; L->n2 = L->c1p / ks;   // stages per PASS (the last layer-1 stage may be partly past c_in: zeros)
     L->w1_stage = (uint32_t)L->c1p * ks * 2; L->w2_stage = (uint32_t)d->c2 * ks * 2;
     uint32_t o = 0;
     L->off_w1 = o; o += L->w1_stage * (uint32_t)L->n1 * (uint32_t)L->npass;       // [pass][stage]
@@ -125,14 +130,24 @@ __device__ __forceinline__ void tmem_ld32_m2(uint32_t taddr, uint32_t* r) {
 }
 
 // One box of the activation tensor map -> shared memory, completing (bytes) on an mbarrier.
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major operand descriptor for a tile whose rows are ONE swizzle span wide (span = ks * 2 bytes: 128 / 64 / 32): 8-row groups
+// 8 * span bytes apart (SBO), leading-dimension field 1 (unused inside a span), version 1, layout type 2 / 4 / 6
+// (cute/arch/mma_sm100_desc.hpp: SWIZZLE_128B / 64B / 32B).  A k-step of 16 halves advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t desc_swizzled(uint32_t saddr, uint32_t span_bytes) {
+    const uint32_t layout = span_bytes == 128 ? 2u : (span_bytes == 64 ? 4u : 6u);
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t hi = ((8u * span_bytes) >> 4) | (1u << 14) | (layout << 29);
+    return ((uint64_t)hi << 32) | lo;
 }
 
 __global__ void __launch_bounds__(M2_THREADS, 1)
 fp_mlp2_kernel(const Mlp2Args a, const __grid_constant__ CUtensorMap xmap) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     const Mlp2Layout& L = a.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* b1 = reinterpret_cast<const float*>(smem + L.off_bias);
@@ -187,7 +202,7 @@ fp_mlp2_kernel(const Mlp2Args a, const __grid_constant__ CUtensorMap xmap) {
                         const uint32_t dst = s_ring + slot * L.stage_bytes, full = bar_full + 8 * slot;
                         if (st < n1) {
                             mbar_expect_tx(full, L.a_bytes + L.w1_stage);            // counts as this thread's arrival
-                            tma_load_3d(dst, &xmap, 0, row0, st * (ks >> 3), full);
+                            tma_load_2d(dst, &xmap, st * ks, row0, full);
                             bulk_g2s(dst + L.a_bytes, a.blob + L.off_w1 + (size_t)(p * n1 + st) * L.w1_stage, L.w1_stage, full);
                         } else {
                             mbar_expect_tx(full, L.w2_stage);
@@ -216,7 +231,7 @@ fp_mlp2_kernel(const Mlp2Args a, const __grid_constant__ CUtensorMap xmap) {
                     if (elect_one_sync()) {
                         const uint32_t sa = s_ring + slot * L.stage_bytes, sw = sa + L.a_bytes;
                         for (int k = 0; k < ksteps; ++k)
-                            umma_f16(tmem_u, desc64(desc_lo(sa + k * (2 * M2_TILE * 16), M2_TILE * 16)),
+                            umma_f16(tmem_u, desc_swizzled(sa + k * 32, (uint32_t)ks * 2),
                                      desc64(desc_lo(sw + k * (2 * L.c1p * 16), L.c1p * 16)), idesc1, (st | k) > 0);
                         umma_commit(bar_empty + 8 * slot);
                         if (st == n1 - 1) umma_commit(bar_d1);
@@ -228,8 +243,13 @@ fp_mlp2_kernel(const Mlp2Args a, const __grid_constant__ CUtensorMap xmap) {
                 if (p == 0 && q > 0) { const long long t0 = M2_T0(); mbar_wait_spin(bar_epi2, (q - 1) & 1); tc_fence_after(); M2_ACC(3, t0); }
                 int have = 0;
                 for (int st = 0; st < n2; ++st, ++g) {
-                    const int pc = (st * ks) / L.piece;
-                    if (pc >= have) { const long long t0 = M2_T0(); mbar_wait_spin(bar_h + 8 * pc, u & 1); tc_fence_after(); have = pc + 1; M2_ACC(2, t0); }
+                    const int pc = ((st + 1) * ks - 1) / L.piece;            // last H piece this stage reads
+                    if (pc >= have) {
+                        const long long t0 = M2_T0();
+                        for (; have <= pc; ++have) mbar_wait_spin(bar_h + 8 * have, u & 1);
+                        tc_fence_after();
+                        M2_ACC(2, t0);
+                    }
                     const uint32_t slot = g % NST, ph = (g / NST) & 1;
                     { const long long t0 = M2_T0(); mbar_wait(bar_full + 8 * slot, ph); M2_ACC(1, t0); }
                     tc_fence_after();
@@ -333,7 +353,7 @@ fp_mlp2_kernel(const Mlp2Args a, const __grid_constant__ CUtensorMap xmap) {
     if (warp == 0) tmem_dealloc(tmem, L.tmem_cols);
 }
 
-// The activation rows as a TMA tensor: (8 channels, rows, c_in / 8) fp16 with strides (2, c_in * 2, 16) bytes, box (8, 128, ks / 8).
+// The activation rows as a TMA tensor: (c_in, rows) fp16, box (ks channels, 128 rows), swizzle span = the box row (ks * 2 bytes).
 static int make_x_map(CUtensorMap* map, const void* x, long long rows, int c_in, int ks) {
     static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     if (!encode) {
@@ -343,12 +363,13 @@ static int make_x_map(CUtensorMap* map, const void* x, long long rows, int c_in,
         if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) { set_error("mlp2_rows: cuTensorMapEncodeTiled not available from the driver"); return 1; }
         encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
     }
-    const cuuint64_t dims[3] = {8, (cuuint64_t)rows, (cuuint64_t)(c_in / 8)};
-    const cuuint64_t strides[2] = {(cuuint64_t)c_in * 2, 16};
-    const cuuint32_t box[3] = {8, (cuuint32_t)M2_TILE, (cuuint32_t)(ks / 8)};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t dims[2] = {(cuuint64_t)c_in, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)c_in * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)ks, (cuuint32_t)M2_TILE};
+    const CUtensorMapSwizzle sw = ks == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (ks == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("mlp2_rows: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return 1; }
     return 0;
 }
@@ -387,7 +408,7 @@ G4D_API int g4d_mlp2_pack_params(const g4d_mlp2_desc* d, const float* w1, const 
         for (int st = 0; st < L.n1; ++st) {
             __half* W = (__half*)(out + L.off_w1 + (size_t)(p * L.n1 + st) * L.w1_stage);
             for (int o = 0; o < L.c1p; ++o)
-                for (int kl = 0; kl < KS; ++kl) put(W, L.c1p, o, kl, w1[(size_t)(p * L.c1p + o) * L.c_in + st * KS + kl]);
+                for (int kl = 0; kl < KS; ++kl) put(W, L.c1p, o, kl, st * KS + kl < L.c_in ? w1[(size_t)(p * L.c1p + o) * L.c_in + st * KS + kl] : 0.f);
         }
         for (int st = 0; st < L.n2; ++st) {
             __half* W = (__half*)(out + L.off_w2 + (size_t)(p * L.n2 + st) * L.w2_stage);
