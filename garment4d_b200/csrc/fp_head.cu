@@ -346,6 +346,8 @@ fp_interp_mlp_kernel(const FpArgs a) {
         mbar_wait(bar_w, 0);                                     // weights + biases resident
         const bool dbgc = a.dbg && blockIdx.x == 0 && cg == 0 && issuer;
         long long t_wait_full = 0, t_wait_done = 0, t_loop0 = dbgc ? clock64() : 0;
+        long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tp = 0, e4a = 0, e4b = 0;   // per layer: issue | wait for the MMAs | epilogue + group barrier
+#define FP_PH(i) do { if (dbgc) { const long long now_ = clock64(); ph[i] += now_ - tp; tp = now_; } } while (0)
         for (int i = cg; i < nseq; i += FP_CG) {
             const long long R = ((long long)blockIdx.x + (long long)i * gridDim.x) * FP_TILE + row;
             const bool live = R < a.total_rows;
@@ -356,6 +358,7 @@ fp_interp_mlp_kernel(const FpArgs a) {
             unsigned char* hbuf = smem + L.off_a + (size_t)ab * L.a_bytes;     // layer-1 operand, then (in place) the hidden activations
             const uint32_t s_h = smem_u32(hbuf);
             // ---- layer 1: A buffer -> D
+            if (dbgc) tp = clock64();
             if (iwarp) {
                 const long long tw0 = dbgc ? clock64() : 0;
                 mbar_wait_spin(bar_full + 8 * ab, use & 1);
@@ -366,12 +369,15 @@ fp_interp_mlp_kernel(const FpArgs a) {
                 }
             }
             __syncwarp();
+            FP_PH(0);
             { const long long tw0 = dbgc ? clock64() : 0;
               mbar_wait(my_done, phase); phase ^= 1;
               if (dbgc) t_wait_done += clock64() - tw0; }
             tc_fence_after();
+            FP_PH(1);
             fp_epilogue_relu(lane_taddr, L.c1, b1, hbuf, row, nullptr, 0);
             tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
+            FP_PH(2);
             // ---- layer 2 (FP output)
             if (iwarp && elect_one_sync()) {
                 fp_issue_layer(tacc, s_h, s_w2, L.c1, L.c2);
@@ -379,18 +385,24 @@ fp_interp_mlp_kernel(const FpArgs a) {
                 umma_commit(my_done);
             }
             __syncwarp();
+            FP_PH(3);
             mbar_wait(my_done, phase); phase ^= 1;
             tc_fence_after();
+            FP_PH(4);
             fp_epilogue_relu(lane_taddr, L.c2, b2, hbuf, row, live ? a.out_feat + ((size_t)cloud * L.c2) * a.n + pt : nullptr, (size_t)a.n);
             tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
+            FP_PH(5);
             if (L.h1) {
                 // ---- head layer 1
                 if (iwarp && elect_one_sync()) { fp_issue_layer(tacc, s_h, s_w3, L.c2, L.h1); umma_commit(my_done); }
                 __syncwarp();
+                FP_PH(6);
                 mbar_wait(my_done, phase); phase ^= 1;
                 tc_fence_after();
+                FP_PH(7);
                 fp_epilogue_relu(lane_taddr, L.h1, b3, hbuf, row, nullptr, 0);
                 tc_fence_before(); fence_proxy_async(); group_bar(bar_id);
+                FP_PH(8);
                 // ---- head layer 2: logits, no activation
                 if (iwarp && elect_one_sync()) {
                     fp_issue_layer(tacc, s_h, s_w4, L.h1, L.h2p);
@@ -398,13 +410,16 @@ fp_interp_mlp_kernel(const FpArgs a) {
                     umma_commit(my_done);
                 }
                 __syncwarp();
+                FP_PH(9);
                 mbar_wait(my_done, phase); phase ^= 1;
                 tc_fence_after();
+                FP_PH(10);
                 float v[16];
                 tmem_ld16(lane_taddr, v);
+                if (dbgc) e4a += clock64() - tp;
                 if (live) {
-                    // (staging these h2 floats per row through shared memory for fully coalesced stores was measured: 0.448 -> 0.477 ms.
-                    // The kernel is bound by the latency of this consumer chain, not by store sectors.)
+                    // (staging these h2 floats per row through shared memory for fully coalesced stores was measured: 0.448 -> 0.477 ms;
+                    // these 8 store instructions take ~2700 cycles to issue behind the producers' gather in the LSU queue, tools/fp_counters.py)
                     float* o = a.out_head + (size_t)R * L.h2;
                     float best = 0.f;
                     int lab = 0;
@@ -418,10 +433,17 @@ fp_interp_mlp_kernel(const FpArgs a) {
                         }
                     if (a.out_label) a.out_label[R] = (unsigned char)lab;
                 }
+                if (dbgc) e4b += clock64() - tp;
                 tc_fence_before(); group_bar(bar_id);            // every warp has drained D: the next tile's layer 1 may overwrite it
+                FP_PH(11);
             }
         }
-        if (dbgc) { a.dbg[2] = t_wait_full; a.dbg[3] = t_wait_done; a.dbg[4] = clock64() - t_loop0; a.dbg[5] = nseq; }
+        if (dbgc) {
+            a.dbg[2] = t_wait_full; a.dbg[3] = t_wait_done; a.dbg[4] = clock64() - t_loop0; a.dbg[5] = nseq;
+            for (int i = 0; i < 12; ++i) a.dbg[8 + i] = ph[i];       // (buffer: >= 22 int64)
+            a.dbg[20] = e4a; a.dbg[21] = e4b;
+        }
+#undef FP_PH
     }
     tc_fence_before();
     __syncthreads();

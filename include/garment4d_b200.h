@@ -182,7 +182,7 @@ int g4d_fp_interp_mlp(const g4d_fp_desc* d, const void* params_dev, int b, int n
  * segmentation labels of modules/mesh_encoder.py:113, written by the kernel's last epilogue. */
 int g4d_fp_interp_mlp_labels(const g4d_fp_desc* d, const void* params_dev, int b, int n, int m, const float* dist2, const int* idx,
                              const void* known_pm, float* out_feat, float* out_head, unsigned char* out_label, void* stream);
-/* debug aid: cycle counters of CTA 0 of the following g4d_fp_interp_mlp launches (buf: >= 8 int64 on the device; NULL = off) */
+/* debug aid: cycle counters of CTA 0 of the following g4d_fp_interp_mlp launches (buf: >= 22 int64 on the device; NULL = off) */
 void g4d_debug_fp_counters(void* buf);
 
 /* y[b,c,:] = max(y[b,c,:] + bias[c], 0) in place (relu = 0: bias only); channel-major (b,c,n), b*c <= 65535.  One-pass

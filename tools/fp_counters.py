@@ -20,7 +20,7 @@ with torch.no_grad():
     f1 = model.FP_modules[1](lx[1], lx[2], lf[1], f2)
     assert model._fused_fp0_head(lx, [None, f1, f2, lf[3]]) is not None
     packed = model._fp0_cache[str(dev)][1]
-    buf = torch.zeros(8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(22, dtype=torch.int64, device=dev)
     for _ in range(2):
         bridge.fp_interp_mlp(packed, lx[0], lx[1], f1)
     torch.cuda.synchronize()
@@ -33,3 +33,11 @@ c = buf.cpu().tolist()
 print(f"NA={os.environ.get('G4D_FP_NA', 'default')}: three_nn + fp_interp_mlp {s.elapsed_time(e):.3f} ms; tiles of CTA 0: {c[5]}")
 print(f"  consumer group 0: loop {c[4]} cycles, issuer waiting for a full A buffer {c[2]} ({100.0 * c[2] / max(c[4], 1):.1f} %), "
       f"waiting for layer-1 MMAs {c[3]} ({100.0 * c[3] / max(c[4], 1):.1f} %)")
+tiles = max(c[5] // 2, 1)
+names = ["L1 issue (incl. wait for A)", "L1 MMAs", "epilogue 1 + barrier", "L2 issue", "L2 MMAs", "epilogue 2 (+ 64 channel stores) + barrier",
+         "L3 issue", "L3 MMAs", "epilogue 3 + barrier", "L4 issue", "L4 MMAs", "epilogue 4 (logits, labels) + barrier"]
+print("  phases of consumer group 0, cycles per tile (its issuing lane):")
+for n, v in zip(names, c[8:20]):
+    print(f"      {n:44s} {v / tiles:8.0f}")
+print(f"      {'sum':44s} {sum(c[8:20]) / tiles:8.0f}")
+print(f"      inside epilogue 4: after tcgen05.ld {c[20] / tiles:.0f}, after the stores {c[21] / tiles:.0f}, after the group barrier {c[19] / tiles:.0f}")
