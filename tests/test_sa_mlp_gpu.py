@@ -98,7 +98,7 @@ def test_training_mode_uses_operator_route_and_backprops(cuda):
     assert all(p.grad is not None for p in mod.parameters())
 
 
-@pytest.mark.parametrize("N", [2048, 1000, 8192])
+@pytest.mark.parametrize("N", [2048, 1000, 8192, 16384])       # 16384: BASELINE config c5 (row-wise pruned FPS, grid searches)
 def test_fused_fp0_head_vs_modules(cuda, N):
     """Encoder forward with the fused FP0+head kernel vs the module-by-module route (cuDNN, true fp32)."""
     from garment4d_b200.encoder import Pointnet2MSGSEG
