@@ -108,7 +108,7 @@ def scatter_add_deterministic(dst: torch.Tensor, n_dst: int, grad: torch.Tensor,
     return out
 
 
-GRID_MIN_POINTS = 2048     # below this the brute-force scans are already cheap
+GRID_MIN_POINTS = 2048     # below this the brute-force scans are already cheap (measured at 1024 points, 256 queries, r = 0.1 / 0.2 on body clouds: brute force 0.145 ms, grid route with its two builds 0.194 ms)
 FPS_PRUNE_MIN_POINTS = 2048
 # "rows": Morton-ordered warp-row pruned kernel (fps_rows.cu, default); "pruned": the cell-sorted thread-per-clump kernel of
 # round 1 (fps_pruned.cu, needs a grid, n <= 8192); "plain": no pruning (fps.cu)
