@@ -330,9 +330,15 @@ class BallQuery(Function):
             grid = _cached_grid(xyz, radius)
             if grid is None:
                 grid = build_grid(xyz, radius)
-            rc = _lib.lib().g4d_ball_query2_grid(B, N, npoint, float(radius), nsample, _lib.ptr(idx), 0.0, 0, None,
-                                                 _lib.ptr(new_xyz), _lib.ptr(grid), _lib.stream_ptr())
-            _lib.check(rc, "g4d_ball_query2_grid")
+            qgrid = None                                     # processing order of the queries (see ball_query_pair)
+            if QUERY_ORDER and npoint >= 256:
+                qgrid = _cached_grid(new_xyz)
+                if qgrid is None:
+                    qgrid = build_grid(new_xyz, radius)
+            rc = _lib.lib().g4d_ball_query2_grid_ordered(B, N, npoint, float(radius), nsample, _lib.ptr(idx), 0.0, 0, None,
+                                                         _lib.ptr(new_xyz), _lib.ptr(grid),
+                                                         _lib.ptr(qgrid) if qgrid is not None else None, _lib.stream_ptr())
+            _lib.check(rc, "g4d_ball_query2_grid_ordered")
         else:
             pointnet2.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
         ctx.mark_non_differentiable(idx)
