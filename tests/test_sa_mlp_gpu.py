@@ -98,6 +98,36 @@ def test_training_mode_uses_operator_route_and_backprops(cuda):
     assert all(p.grad is not None for p in mod.parameters())
 
 
+def test_training_mode_channels_last_layers_equal_the_nchw_ones(cuda):
+    """Training mode runs torch's conv / BatchNorm / ReLU layers in channels_last memory (pytorch_utils.SharedMLP): same outputs,
+    same gradients as the NCHW layers, batch statistics included."""
+    from garment4d_b200.pointnet2 import pytorch_utils as ptu
+    res = {}
+    for cl in (True, False):
+        torch.manual_seed(5)
+        mod = pm.PointnetSAModuleMSG(npoint=64, radii=[0.2, 0.4], nsamples=[16, 32], mlps=[[6, 16, 16, 32], [6, 32, 32, 64]], bn=True).to(cuda).train()
+        xyz = torch.from_numpy(clouds(9, 3, 512, "body")).to(cuda)
+        feats = torch.randn(3, 6, 512, device=cuda, requires_grad=True)
+        old, old_tf32 = ptu.SharedMLP.channels_last_training, torch.backends.cudnn.allow_tf32
+        ptu.SharedMLP.channels_last_training = cl
+        torch.backends.cudnn.allow_tf32 = False              # true fp32 in both layouts (TF32 kernels differ in rounding order)
+        try:
+            _, out = mod(xyz, feats)
+            (out * torch.linspace(0.5, 1.5, out.shape[1], device=cuda)[None, :, None]).sum().backward()
+        finally:
+            ptu.SharedMLP.channels_last_training = old
+            torch.backends.cudnn.allow_tf32 = old_tf32
+        res[cl] = (out.detach(), feats.grad.detach(), [p.grad.detach().clone() for p in mod.parameters()],
+                   [b.detach().clone() for n, b in mod.named_buffers() if "running" in n])
+    a, b = res[True], res[False]
+    _close(a[0], b[0], tol=1e-4)
+    _close(a[1], b[1], tol=1e-3)
+    for ga, gb in zip(a[2], b[2]):
+        _close(ga, gb, tol=1e-3)
+    for ra, rb in zip(a[3], b[3]):
+        _close(ra, rb, tol=1e-5)
+
+
 @pytest.mark.parametrize("N", [2048, 1000, 8192, 16384])       # 16384: BASELINE config c5 (row-wise pruned FPS, grid searches)
 def test_fused_fp0_head_vs_modules(cuda, N):
     """Encoder forward with the fused FP0+head kernel vs the module-by-module route (cuDNN, true fp32)."""
