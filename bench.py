@@ -484,7 +484,8 @@ def train_arm(torch, dist, args, dev, rank, world, seqs, T, N, seed, barrier, ma
         return loss
 
     progress(rank, "train arm: warm-up")
-    one_step()
+    for _ in range(2):                                             # the library picks its convolution / BatchNorm kernels in the first passes
+        one_step()
     barrier("train: warm-up done")
     steps = max(1, args.train_steps)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
